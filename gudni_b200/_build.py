@@ -1,0 +1,72 @@
+"""In-tree builds of the native pieces (no JIT cache: the .so files travel with the repo snapshot).
+
+  libgudni_b200.so  CUDA kernels + C-ABI shim        nvcc, sm_100a only
+  libgudni_host.so  harness: wire-format producer    g++
+"""
+import os
+import shutil
+import subprocess
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(ROOT)
+CSRC = os.path.join(ROOT, "csrc")
+LIB_CUDA = os.path.join(ROOT, "libgudni_b200.so")
+LIB_HOST = os.path.join(ROOT, "libgudni_host.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # parity contract with the oracle: IEEE f32, no FMA contraction, IEEE division / sqrt
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _host_cxx():
+    # the image exports CXX=/opt/gcc/bin/g++, a wrapper that lacks libgomp.spec; prefer the system one
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources(dirpath, exts):
+    out = []
+    for base, _, files in os.walk(dirpath):
+        out += [os.path.join(base, f) for f in files if f.endswith(exts)]
+    return sorted(out)
+
+
+def build_host(force=False, verbose=False):
+    src = [os.path.join(CSRC, "host", "scene.cpp")]
+    deps = _sources(os.path.join(CSRC, "host"), (".cpp", ".hpp")) + [os.path.join(REPO, "include", "gudni_b200.h")]
+    if not force and _newer(LIB_HOST, deps):
+        return LIB_HOST
+    cmd = [_host_cxx(), "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", LIB_HOST] + src
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_HOST
+
+
+def build_cuda(force=False, verbose=False, extra=()):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = _sources(CSRC, (".cu",))
+    deps = src + _sources(CSRC, (".cuh", ".h")) + [os.path.join(REPO, "include", "gudni_b200.h")]
+    if not force and _newer(LIB_CUDA, deps):
+        return LIB_CUDA
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(REPO, "include"), "-o", LIB_CUDA] + src
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_CUDA
+
+
+def build_oracle(force=False, verbose=False):
+    odir = os.path.join(REPO, "oracle")
+    cmd = ["make", "-C", odir] + (["-B"] if force else [])
+    subprocess.run(cmd, check=True, stdout=None if verbose else subprocess.DEVNULL)
+    return os.path.join(odir, "libgudni_oracle.so")

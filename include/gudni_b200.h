@@ -1,0 +1,209 @@
+/* gudni_b200.h — C ABI of libgudni_b200.so, the sm_100a rasterizer that stands in for
+ * Gudni's OpenCL host layer + Kernels.cl.
+ *
+ * Every entry point below replaces a Haskell function of the reference whose body calls CLUtil /
+ * OpenCL today (the reference has no FFI for this path).  Paths are relative
+ * to /root/reference/src/Graphics/Gudni/.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature; pointers named `dev_*` are device pointers,
+ *     all others are host pointers owned by the caller and only read during the call.
+ *   - every function returns GUDNI_OK (0) or a negative gudni_status; the message for the last
+ *     failure on a context is available from gudni_b200_last_error().  Nothing aborts or throws.
+ *   - one caller thread per context; calls may block (safe for `foreign import ccall safe`).
+ *   - there is no CPU fallback: if no sm_100-class device is usable, init fails.
+ */
+#ifndef GUDNI_B200_H
+#define GUDNI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Wire formats (little endian).  These are the byte layouts the Haskell `StorableM` instances
+ * poke and `Kernels.cl` reads; they are the ABI contract.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* RasterSpec — OpenCL/Rasterizer.hs:37-50, derived in OpenCL/Setup.hs:71-87. */
+typedef struct gudni_spec {
+    int32_t max_tile_size;        /* specMaxTileSize      (pixels, power of two)            */
+    int32_t threads_per_tile;     /* specThreadsPerTile   (power of two, 32..1024)          */
+    int32_t max_tiles_per_call;   /* specMaxTilesPerCall  (job packing only)                */
+    int32_t max_thresholds;       /* specMaxThresholds    (MAXTHRESHOLDS, per column-thread)*/
+    int32_t max_strands_per_tile; /* specMaxStrandsPerTile                                  */
+    int32_t max_shapes;           /* specMaxShapes        (MAXSHAPE, <= 127)                */
+} gudni_spec;
+
+/* Shape GeoReference — Raster/Types.hs:159-168 / Kernels.cl:318-321.  16 bytes. */
+typedef struct gudni_shape {
+    uint64_t tag;          /* ShapeTag: Raster/Constants.hs:74-89                            */
+    uint32_t geo_start;    /* offset into the geometry heap in 16-byte units                 */
+    uint32_t num_strands;
+} gudni_shape;
+
+#define GUDNI_TAG_SUBSTANCETYPE_MASK  0xC000000000000000ull
+#define GUDNI_TAG_SUBSTANCE_SOLID     0x8000000000000000ull
+#define GUDNI_TAG_SUBSTANCE_PICTURE   0x4000000000000000ull
+#define GUDNI_TAG_COMPOUND_MASK       0x3000000000000000ull
+#define GUDNI_TAG_COMPOUND_CONTINUE   0x1000000000000000ull
+#define GUDNI_TAG_COMPOUND_ADD        0x2000000000000000ull
+#define GUDNI_TAG_COMPOUND_SUBTRACT   0x3000000000000000ull
+#define GUDNI_TAG_SUBSTANCEID_MASK    0x0FFFFFFFFFFFFFFFull
+
+/* Tile (Slice (Shape GeoReference), Int) — Raster/Types.hs:176-198 / Kernels.cl:335-341. 32 B. */
+typedef struct gudni_tile {
+    int32_t  left, top, right, bottom; /* tileBox in pixels                                   */
+    int16_t  h_depth;                  /* log2 width                                          */
+    int16_t  v_depth;                  /* log2 height                                         */
+    int32_t  column_allocation;        /* first column-thread id of the tile inside its job   */
+    uint32_t shape_start;              /* slice into the job's shape array                    */
+    uint32_t shape_count;
+} gudni_tile;
+
+/* PictureUsage PictureMemoryReference — Figure/Picture.hs:183-199 / Kernels.cl:349-354. 24 B. */
+typedef struct gudni_picture_use {
+    float    translate_x, translate_y;
+    int32_t  width, height;
+    uint32_t mem_offset;               /* byte offset into the picture heap                   */
+    float    scale;
+} gudni_picture_use;
+
+/* Un-binned shape entry = Shape ShapeEntry (Raster/Types.hs:139-157): what `addShapeToTree`
+ * (Raster/TileTree.hs:113) receives.  Not a reference wire format (Haskell never serialises it);
+ * this is the level-2 input that moves tile binning behind the shim.  32 bytes. */
+typedef struct gudni_shape_entry {
+    uint64_t tag;
+    uint32_t geo_start;
+    uint32_t num_strands;
+    float    left, top, right, bottom; /* shapeBox (includes control points)                  */
+} gudni_shape_entry;
+
+/* Per-frame statistics — replaces the reference's putStrLn/`tr` logging. */
+typedef struct gudni_stats {
+    int64_t n_tiles;            /* leaf tiles rendered                                        */
+    int64_t n_shape_refs;       /* sum over tiles of shape_count                              */
+    int64_t n_thresholds;       /* thresholds kept by the generate phase, summed over threads */
+    int64_t n_spilled_threads;  /* column-threads that left the on-chip queue for the HBM one */
+    int64_t n_overflow_threads; /* column-threads that exceeded max_thresholds (UB in ref.)   */
+    int64_t algorithmic_bytes;  /* A(frame), SURVEY.md §8(d)                                  */
+    float   ms_upload, ms_bin, ms_raster, ms_download; /* CUDA-event stage times              */
+} gudni_stats;
+
+typedef enum gudni_status {
+    GUDNI_OK            =  0,
+    GUDNI_ERR_ARGUMENT  = -1,
+    GUDNI_ERR_NO_DEVICE = -2,
+    GUDNI_ERR_CUDA      = -3,
+    GUDNI_ERR_STATE     = -4,
+    GUDNI_ERR_OOM       = -5
+} gudni_status;
+
+typedef struct gudni_ctx gudni_ctx;
+
+/* ------------------------------------------------------------------------------------------------
+ * Entry points
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces setupOpenCL (OpenCL/Setup.hs:102-147) + determineRasterSpec (:71-87).
+ * `device` = CUDA ordinal or -1 for the current device.  `want` may be NULL (canonical spec:
+ * 256,256,256,1024,1022,127).  `got` receives the spec in force; the Haskell side reads
+ * max_tile_size / threads_per_tile / max_tiles_per_call / max_strands_per_tile from it
+ * (Application.hs:224, Raster/Serialize.hs:131, OpenCL/CallKernels.hs:251-252). */
+int gudni_b200_init(int device, const gudni_spec* want, gudni_spec* got, gudni_ctx** out);
+
+/* Replaces the frame-constant uploads of queueRasterJobs (OpenCL/CallKernels.hs:223-242:
+ * pileToBuffer x4 + vectorToBuffer) and picks up bitmapSize / frameCount / background of
+ * `raster` (:189-197) and generateCall (:159-171).  The random field is not taken: it is inert
+ * (STOCHASTIC_FACTOR = 0, Raster/Constants.hs:54). */
+int gudni_b200_frame_begin(gudni_ctx* ctx,
+                           const void* geometry, size_t geometry_bytes,
+                           const float* substances /* 4 floats each */, int n_substances,
+                           const uint8_t* picture_bytes, size_t n_picture_bytes,
+                           const gudni_picture_use* picture_uses, int n_picture_uses,
+                           const float background_rgba[4],
+                           int width, int height, int frame_number);
+
+/* Restrict this context to canvas rows [row_begin, row_end) (whole rows of root tiles).  Used by
+ * the multi-GPU strip partition (no reference counterpart: one OpenCLState = one device,
+ * OpenCL/Setup.hs:118-120).  row_begin = 0, row_end = height restores the full frame. Must be
+ * called after frame_begin and before any raster call of the frame. */
+int gudni_b200_frame_strip(gudni_ctx* ctx, int row_begin, int row_end);
+
+/* Level 1 — exact stand-in for `raster`/`generateCall` (OpenCL/CallKernels.hs:182-206, 88-179):
+ * one RasterJob whose tiles were binned by the caller (Raster/Job.hs:132-178).  Asynchronous:
+ * returns once the job is enqueued. */
+int gudni_b200_raster_job(gudni_ctx* ctx,
+                          const gudni_shape* shapes, int n_shapes,
+                          const gudni_tile* tiles, int n_tiles,
+                          int columns_allocated, int job_index);
+
+/* Level 2 — tile binning behind the shim: replaces buildTileTree/addShapeToTree
+ * (Raster/TileTree.hs:81-190), traverseTileTree (:193-204), accumulateRasterJobs
+ * (Raster/Job.hs:151-178) and the per-job loop of queueRasterJobs.  Entries are in scene order
+ * (first = top-most), already culled against the canvas (Raster/Serialize.hs:97-104). */
+int gudni_b200_raster_scene(gudni_ctx* ctx, const gudni_shape_entry* entries, int n_entries);
+
+/* Replaces the OutputPtr read-back (OpenCL/Instances.hs:60-75): waits for the frame, copies the
+ * BGRA8 words (B | G<<8 | R<<16 | 0xFF<<24) of the context's rows into `out_bgra`
+ * (width * (row_end-row_begin) words, may be NULL to leave the frame on the device) and fills
+ * `stats` (may be NULL). */
+int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats);
+
+/* Device-side access for callers that keep data on the GPU (bench, multi-GPU gather).  The frame
+ * pointer stays valid until the next frame_begin with a different size, or destroy. */
+int gudni_b200_frame_device_ptr(gudni_ctx* ctx, void** dev_bgra, size_t* n_bytes);
+/* Redirect pixel stores of this context to a caller-owned device buffer holding the full canvas
+ * (width*height words; row y of the canvas at word y*width) — e.g. a peer GPU's frame mapped
+ * through CUDA IPC, so strips land on the presenting GPU over NVLink without a separate gather.
+ * NULL restores the context's own frame buffer. */
+int gudni_b200_frame_target(gudni_ctx* ctx, void* dev_canvas_bgra);
+/* CUDA-IPC plumbing for the above (one process per GPU). `handle` is 64 bytes. */
+int gudni_b200_ipc_export_frame(gudni_ctx* ctx, void* handle_64b);
+int gudni_b200_ipc_open(gudni_ctx* ctx, const void* handle_64b, void** dev_ptr);
+int gudni_b200_ipc_close(gudni_ctx* ctx, void* dev_ptr);
+
+/* Same as frame_begin/raster_scene but with inputs already resident on the device
+ * (pointers previously obtained from gudni_b200_device_alloc).  Used by bench.py's
+ * inputs-in-HBM leg. */
+int gudni_b200_device_alloc(gudni_ctx* ctx, size_t bytes, void** dev_ptr);
+int gudni_b200_device_free(gudni_ctx* ctx, void* dev_ptr);
+int gudni_b200_upload(gudni_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+int gudni_b200_download(gudni_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+int gudni_b200_frame_begin_device(gudni_ctx* ctx,
+                                  const void* dev_geometry, size_t geometry_bytes,
+                                  const void* dev_substances, int n_substances,
+                                  const void* dev_picture_bytes, size_t n_picture_bytes,
+                                  const void* dev_picture_uses, int n_picture_uses,
+                                  const float background_rgba[4],
+                                  int width, int height, int frame_number);
+int gudni_b200_raster_scene_device(gudni_ctx* ctx, const void* dev_entries, int n_entries);
+/* Waits for all queued work of the context. */
+int gudni_b200_sync(gudni_ctx* ctx);
+/* Milliseconds of device time between the first and last kernel of the last frame. */
+int gudni_b200_last_frame_ms(gudni_ctx* ctx, float* ms);
+/* Number of kernels this library launched on the context since init. */
+int gudni_b200_launch_count(gudni_ctx* ctx, int64_t* n);
+
+/* Parity taps (tests only; no reference counterpart — the reference's DEBUG_OUTPUT printf,
+ * Kernels.cl:54-68, is the closest).  When enabled before a raster call, the generate phase
+ * records, per column-thread id (column_allocation + column, jobs laid end to end), the queue
+ * length qSlice.sLength and ShapeState.shapeBits it would have stored (Kernels.cl:2078-2080). */
+int gudni_b200_debug_enable(gudni_ctx* ctx, int on);
+int gudni_b200_debug_thread_counts(gudni_ctx* ctx, int32_t* n_thresholds, int32_t* shape_bits,
+                                   int64_t capacity, int64_t* n_threads);
+/* Tiles and per-tile shape lists produced by the last level-2 binning, in job order. */
+int gudni_b200_debug_binned(gudni_ctx* ctx, gudni_tile* tiles, int64_t tile_capacity,
+                            int64_t* n_tiles, gudni_shape* shapes, int64_t shape_capacity,
+                            int64_t* n_shapes);
+
+const char* gudni_b200_last_error(gudni_ctx* ctx);
+void gudni_b200_destroy(gudni_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUDNI_B200_H */
