@@ -1,0 +1,123 @@
+// context.cuh — the rasterizer context behind the C ABI (include/gudni_b200.h): device buffers,
+// stream, events, error text.  Replaces what `Rasterizer` / `OpenCLState` hold in the reference
+// (OpenCL/Rasterizer.hs:52-60) and the per-job clCreateBuffer/clReleaseMemObject traffic of
+// generateCall (OpenCL/CallKernels.hs:124-127, 175-178): every buffer here is allocated once,
+// grown geometrically, and reused across jobs and frames.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/gudni_b200.h"
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    template <class T>
+    T* as() const { return static_cast<T*>(ptr); }
+};
+
+struct gudni_ctx {
+    int device = 0;
+    gudni_spec spec{};
+    int computeDepth = 8;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // frame constants
+    DevBuf geometry, substances, pictures, pictureUses;
+    const void *geometryPtr = nullptr, *substancesPtr = nullptr, *picturesPtr = nullptr, *pictureUsesPtr = nullptr;
+    size_t geometryBytes = 0, pictureBytes = 0;
+    int nSubstances = 0, nPictureUses = 0;
+    float background[4] = {0, 0, 0, 1};
+    int width = 0, height = 0, frameNumber = 0;
+    int rowBegin = 0, rowEnd = 0;
+    bool inFrame = false;
+
+    // per-frame tile / shape arrays (all jobs laid end to end)
+    DevBuf shapes, tiles, tileThreadBase;
+    int64_t nShapes = 0, nTiles = 0, nColumns = 0;
+    int64_t rasteredTiles = 0;   // tiles already covered by a raster launch this frame
+
+    // output
+    DevBuf frame;
+    void* externalTarget = nullptr;   // gudni_b200_frame_target
+
+    // counters / spill
+    DevBuf counters;        // 8 x u64
+    DevBuf spillList;       // u32 per spilled thread
+    int spillCapacity = 0;
+    DevBuf spillThr, spillHdr;
+    int spillSlots = 0;
+
+    // taps
+    bool debug = false;
+    DevBuf dbgThresholds, dbgShapeBits;
+
+    // binning (level 2)
+    DevBuf entries;
+    const void* entriesPtr = nullptr;
+    int nEntries = 0;
+    bool binUsed = false;
+    DevBuf binWork[8];
+    DevBuf binCounters;
+
+    // pinned staging for host transfers
+    void* pinned = nullptr;
+    size_t pinnedCap = 0;
+
+    // timing
+    cudaEvent_t evFrameBegin = nullptr, evUploadDone = nullptr, evBinDone = nullptr, evRasterDone = nullptr,
+                evDownloadDone = nullptr, evFirstKernel = nullptr;
+    bool firstKernelRecorded = false;
+    float lastFrameMs = 0.f;
+    gudni_stats lastStats{};
+};
+
+inline int ctxFail(gudni_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define GUDNI_CUDA_TRY(ctx, expr)                                                                         \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return ctxFail((ctx), e_ == cudaErrorMemoryAllocation ? GUDNI_ERR_OOM : GUDNI_ERR_CUDA,      \
+                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+    } while (0)
+
+// Grow `b` to at least `bytes` (geometric growth).  Contents are preserved when `keep` > 0 bytes.
+inline int devEnsure(gudni_ctx* ctx, DevBuf& b, size_t bytes, size_t keep = 0) {
+    if (bytes <= b.cap) return GUDNI_OK;
+    size_t ncap = b.cap ? b.cap : 4096;
+    while (ncap < bytes) ncap *= 2;
+    void* np = nullptr;
+    GUDNI_CUDA_TRY(ctx, cudaMalloc(&np, ncap));
+    if (keep && b.ptr) {
+        GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(np, b.ptr, keep, cudaMemcpyDeviceToDevice, ctx->stream));
+        GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    } else if (b.ptr) {
+        GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = np;
+    b.cap = ncap;
+    return GUDNI_OK;
+}
+
+#define GUDNI_TRY(expr)            \
+    do {                           \
+        int rc_ = (expr);          \
+        if (rc_ != GUDNI_OK) return rc_; \
+    } while (0)

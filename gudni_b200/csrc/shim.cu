@@ -1,0 +1,478 @@
+// shim.cu — the C ABI of include/gudni_b200.h.  Each entry point names the reference function it
+// stands in for (paths relative to /root/reference/src/Graphics/Gudni/).
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "binning.cuh"
+#include "context.cuh"
+#include "raster_kernels.cuh"
+
+using gudni_dev::FrameParams;
+
+namespace {
+
+constexpr int kSpillListCapacity = 1 << 22;   // column-threads that may leave the on-chip queue per frame
+constexpr int kSpillSlots = 148 * 128;        // HBM queue slots of the replay kernel (one CTA of 128 per SM)
+
+bool isPow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+int log2i(int x) { int d = 0; while ((1 << d) < x) d++; return d; }
+
+FrameParams makeParams(gudni_ctx* ctx) {
+    FrameParams P{};
+    P.geometry = static_cast<const uint8_t*>(ctx->geometryPtr);
+    P.shapes = ctx->shapes.as<gudni_shape>();
+    P.tiles = ctx->tiles.as<gudni_tile>();
+    P.tileThreadBase = ctx->tileThreadBase.as<int32_t>();
+    P.substances = static_cast<const float4*>(ctx->substancesPtr);
+    P.pictureData = static_cast<const uint8_t*>(ctx->picturesPtr);
+    P.pictureUses = static_cast<const gudni_picture_use*>(ctx->pictureUsesPtr);
+    if (ctx->externalTarget) {
+        P.out = static_cast<uint32_t*>(ctx->externalTarget);
+        P.rowOrigin = 0;
+    } else {
+        P.out = ctx->frame.as<uint32_t>();
+        P.rowOrigin = ctx->rowBegin;
+    }
+    P.background = make_float4(ctx->background[0], ctx->background[1], ctx->background[2], ctx->background[3]);
+    P.width = ctx->width;
+    P.height = ctx->height;
+    P.rowBegin = ctx->rowBegin;
+    P.rowEnd = ctx->rowEnd;
+    P.computeDepth = ctx->computeDepth;
+    P.maxShape = ctx->spec.max_shapes;
+    P.maxThresholds = ctx->spec.max_thresholds;
+    P.dbgThresholds = ctx->debug ? ctx->dbgThresholds.as<int32_t>() : nullptr;
+    P.dbgShapeBits = ctx->debug ? ctx->dbgShapeBits.as<int32_t>() : nullptr;
+    P.counters = ctx->counters.as<unsigned long long>();
+    P.spillList = ctx->spillList.as<unsigned long long>();
+    P.spillCapacity = ctx->spillCapacity;
+    return P;
+}
+
+int ensureFrameBuffer(gudni_ctx* ctx) {
+    if (ctx->externalTarget) return GUDNI_OK;
+    size_t bytes = (size_t)ctx->width * (size_t)(ctx->rowEnd - ctx->rowBegin) * 4;
+    return devEnsure(ctx, ctx->frame, std::max<size_t>(bytes, 4));
+}
+
+int ensureDebug(gudni_ctx* ctx, int64_t columnsBefore, int64_t columnsAfter) {
+    if (!ctx->debug) return GUDNI_OK;
+    GUDNI_TRY(devEnsure(ctx, ctx->dbgThresholds, (size_t)columnsAfter * 4, (size_t)columnsBefore * 4));
+    GUDNI_TRY(devEnsure(ctx, ctx->dbgShapeBits, (size_t)columnsAfter * 4, (size_t)columnsBefore * 4));
+    size_t n = (size_t)(columnsAfter - columnsBefore) * 4;
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->dbgThresholds.as<char>() + columnsBefore * 4, 0xFF, n, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->dbgShapeBits.as<char>() + columnsBefore * 4, 0xFF, n, ctx->stream));
+    return GUDNI_OK;
+}
+
+void markFirstKernel(gudni_ctx* ctx) {
+    if (!ctx->firstKernelRecorded) {
+        cudaEventRecord(ctx->evFirstKernel, ctx->stream);
+        ctx->firstKernelRecorded = true;
+    }
+}
+
+int beginFrameCommon(gudni_ctx* ctx, const float bg[4], int width, int height, int frame) {
+    if (width <= 0 || height <= 0) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "frame_begin: bad bitmap size %dx%d", width, height);
+    std::memcpy(ctx->background, bg, 16);
+    ctx->width = width;
+    ctx->height = height;
+    ctx->frameNumber = frame;
+    ctx->rowBegin = 0;
+    ctx->rowEnd = height;
+    ctx->nShapes = ctx->nTiles = ctx->nColumns = 0;
+    ctx->rasteredTiles = 0;
+    ctx->firstKernelRecorded = false;
+    ctx->binUsed = false;
+    ctx->inFrame = true;
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, 64, ctx->stream));
+    return GUDNI_OK;
+}
+
+int uploadTo(gudni_ctx* ctx, DevBuf& buf, const void* src, size_t bytes) {
+    GUDNI_TRY(devEnsure(ctx, buf, std::max<size_t>(bytes, 16)));
+    if (bytes) GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(buf.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return GUDNI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// setupOpenCL + determineRasterSpec, OpenCL/Setup.hs:71-87, 102-147
+int gudni_b200_init(int device, const gudni_spec* want, gudni_spec* got, gudni_ctx** out) {
+    if (!out) return GUDNI_ERR_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return GUDNI_ERR_NO_DEVICE;
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return GUDNI_ERR_NO_DEVICE;
+    }
+    if (device >= count) return GUDNI_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GUDNI_ERR_NO_DEVICE;
+    if (prop.major < 10) return GUDNI_ERR_NO_DEVICE;   // sm_100a code only; there is no fallback path
+    gudni_ctx* ctx = new (std::nothrow) gudni_ctx();
+    if (!ctx) return GUDNI_ERR_OOM;
+    ctx->device = device;
+    gudni_spec spec = {256, 256, 256, 1024, 1022, 127};   // canonical spec, BASELINE.md §3
+    if (want) spec = *want;
+    if (!isPow2(spec.max_tile_size) || !isPow2(spec.threads_per_tile) || spec.threads_per_tile < 32 ||
+        spec.threads_per_tile > 1024 || spec.max_tile_size < 8 || spec.max_thresholds < 4 || spec.max_shapes < 1 ||
+        spec.max_shapes > gudni_dev::kMaxShapeLimit || spec.max_tiles_per_call < 1 || spec.max_strands_per_tile < 1) {
+        delete ctx;
+        return GUDNI_ERR_ARGUMENT;
+    }
+    ctx->spec = spec;
+    ctx->computeDepth = log2i(spec.threads_per_tile);
+    if (got) *got = spec;
+    auto fail = [&](int code) { gudni_b200_destroy(ctx); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
+    cudaEvent_t* evs[] = {&ctx->evFrameBegin, &ctx->evUploadDone, &ctx->evBinDone, &ctx->evRasterDone,
+                          &ctx->evDownloadDone, &ctx->evFirstKernel};
+    for (cudaEvent_t* e : evs)
+        if (cudaEventCreate(e) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
+    if (devEnsure(ctx, ctx->counters, 64) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
+    ctx->spillCapacity = kSpillListCapacity;
+    if (devEnsure(ctx, ctx->spillList, (size_t)kSpillListCapacity * 8) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
+    ctx->spillSlots = kSpillSlots;
+    if (devEnsure(ctx, ctx->spillThr, (size_t)kSpillSlots * spec.max_thresholds * 16) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
+    if (devEnsure(ctx, ctx->spillHdr, (size_t)kSpillSlots * spec.max_thresholds * 4) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
+    *out = ctx;
+    return GUDNI_OK;
+}
+
+void gudni_b200_destroy(gudni_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->geometry, &ctx->substances, &ctx->pictures, &ctx->pictureUses, &ctx->shapes, &ctx->tiles,
+                      &ctx->tileThreadBase, &ctx->frame, &ctx->counters, &ctx->spillList, &ctx->spillThr, &ctx->spillHdr,
+                      &ctx->dbgThresholds, &ctx->dbgShapeBits, &ctx->entries, &ctx->binCounters};
+    for (DevBuf* b : bufs)
+        if (b->ptr) cudaFree(b->ptr);
+    for (DevBuf& b : ctx->binWork)
+        if (b.ptr) cudaFree(b.ptr);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEvent_t evs[] = {ctx->evFrameBegin, ctx->evUploadDone, ctx->evBinDone, ctx->evRasterDone, ctx->evDownloadDone,
+                         ctx->evFirstKernel};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    delete ctx;
+}
+
+const char* gudni_b200_last_error(gudni_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+// queueRasterJobs' frame-constant uploads, OpenCL/CallKernels.hs:229-235
+int gudni_b200_frame_begin(gudni_ctx* ctx, const void* geometry, size_t geometry_bytes, const float* substances,
+                           int n_substances, const uint8_t* picture_bytes, size_t n_picture_bytes,
+                           const gudni_picture_use* picture_uses, int n_picture_uses, const float background_rgba[4],
+                           int width, int height, int frame_number) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if ((geometry_bytes && !geometry) || (n_substances && !substances) || (n_picture_bytes && !picture_bytes) ||
+        (n_picture_uses && !picture_uses) || !background_rgba || n_substances < 0 || n_picture_uses < 0)
+        return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "frame_begin: null or negative-sized input");
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evFrameBegin, ctx->stream));
+    GUDNI_TRY(beginFrameCommon(ctx, background_rgba, width, height, frame_number));
+    GUDNI_TRY(uploadTo(ctx, ctx->geometry, geometry, geometry_bytes));
+    GUDNI_TRY(uploadTo(ctx, ctx->substances, substances, (size_t)n_substances * 16));
+    GUDNI_TRY(uploadTo(ctx, ctx->pictures, picture_bytes, n_picture_bytes));
+    GUDNI_TRY(uploadTo(ctx, ctx->pictureUses, picture_uses, (size_t)n_picture_uses * sizeof(gudni_picture_use)));
+    ctx->geometryPtr = ctx->geometry.ptr;
+    ctx->substancesPtr = ctx->substances.ptr;
+    ctx->picturesPtr = ctx->pictures.ptr;
+    ctx->pictureUsesPtr = ctx->pictureUses.ptr;
+    ctx->geometryBytes = geometry_bytes;
+    ctx->pictureBytes = n_picture_bytes;
+    ctx->nSubstances = n_substances;
+    ctx->nPictureUses = n_picture_uses;
+    GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evUploadDone, ctx->stream));
+    return GUDNI_OK;
+}
+
+int gudni_b200_frame_begin_device(gudni_ctx* ctx, const void* dev_geometry, size_t geometry_bytes,
+                                  const void* dev_substances, int n_substances, const void* dev_picture_bytes,
+                                  size_t n_picture_bytes, const void* dev_picture_uses, int n_picture_uses,
+                                  const float background_rgba[4], int width, int height, int frame_number) {
+    if (!ctx || !background_rgba) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evFrameBegin, ctx->stream));
+    GUDNI_TRY(beginFrameCommon(ctx, background_rgba, width, height, frame_number));
+    ctx->geometryPtr = dev_geometry;
+    ctx->substancesPtr = dev_substances;
+    ctx->picturesPtr = dev_picture_bytes;
+    ctx->pictureUsesPtr = dev_picture_uses;
+    ctx->geometryBytes = geometry_bytes;
+    ctx->pictureBytes = n_picture_bytes;
+    ctx->nSubstances = n_substances;
+    ctx->nPictureUses = n_picture_uses;
+    GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evUploadDone, ctx->stream));
+    return GUDNI_OK;
+}
+
+int gudni_b200_frame_strip(gudni_ctx* ctx, int row_begin, int row_end) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if (!ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "frame_strip outside a frame");
+    if (ctx->nTiles) return ctxFail(ctx, GUDNI_ERR_STATE, "frame_strip after raster calls");
+    const int tileRows = ctx->spec.max_tile_size;
+    if (row_begin < 0 || row_end > ctx->height || row_begin >= row_end || (row_begin % tileRows) != 0 ||
+        (row_end != ctx->height && (row_end % tileRows) != 0))
+        return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "frame_strip: rows [%d,%d) are not whole root-tile rows of %d", row_begin,
+                       row_end, tileRows);
+    ctx->rowBegin = row_begin;
+    ctx->rowEnd = row_end;
+    return GUDNI_OK;
+}
+
+// raster + generateCall, OpenCL/CallKernels.hs:88-206
+int gudni_b200_raster_job(gudni_ctx* ctx, const gudni_shape* shapes, int n_shapes, const gudni_tile* tiles, int n_tiles,
+                          int columns_allocated, int job_index) {
+    (void)job_index;   // only feeds the inert random field in the reference (K.cl:1713)
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if (!ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_job outside a frame");
+    if (n_shapes < 0 || n_tiles < 0 || (n_shapes && !shapes) || (n_tiles && !tiles) || columns_allocated < 0)
+        return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_job: null or negative-sized input");
+    if (n_tiles == 0) return GUDNI_OK;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int G = ctx->spec.threads_per_tile;
+    // rebase the job onto the frame-wide arrays; validate what the kernels index with
+    std::vector<gudni_tile> t(tiles, tiles + n_tiles);
+    std::vector<int32_t> base(n_tiles);
+    for (int i = 0; i < n_tiles; i++) {
+        const gudni_tile& ti = tiles[i];
+        if ((uint64_t)ti.shape_start + ti.shape_count > (uint64_t)n_shapes)
+            return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_job: tile %d shape slice out of range", i);
+        if (ti.column_allocation < 0 || (int64_t)ti.column_allocation + G > (int64_t)columns_allocated)
+            return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_job: tile %d column allocation out of range", i);
+        if (ti.h_depth < 0 || ti.h_depth > 15 || ti.v_depth < 0 || ti.v_depth > 15)
+            return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_job: tile %d depth out of range", i);
+        t[i].shape_start = ti.shape_start + (uint32_t)ctx->nShapes;
+        base[i] = (int32_t)(ctx->nColumns + ti.column_allocation);
+    }
+    GUDNI_TRY(devEnsure(ctx, ctx->shapes, (size_t)(ctx->nShapes + n_shapes) * 16 + 16, (size_t)ctx->nShapes * 16));
+    GUDNI_TRY(devEnsure(ctx, ctx->tiles, (size_t)(ctx->nTiles + n_tiles) * 32, (size_t)ctx->nTiles * 32));
+    GUDNI_TRY(devEnsure(ctx, ctx->tileThreadBase, (size_t)(ctx->nTiles + n_tiles) * 4, (size_t)ctx->nTiles * 4));
+    GUDNI_TRY(ensureFrameBuffer(ctx));
+    GUDNI_TRY(ensureDebug(ctx, ctx->nColumns, ctx->nColumns + columns_allocated));
+    if (n_shapes)
+        GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->shapes.as<gudni_shape>() + ctx->nShapes, shapes, (size_t)n_shapes * 16,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tiles.as<gudni_tile>() + ctx->nTiles, t.data(), (size_t)n_tiles * 32,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tileThreadBase.as<int32_t>() + ctx->nTiles, base.data(), (size_t)n_tiles * 4,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+    const int tileBase = (int)ctx->nTiles;
+    ctx->nShapes += n_shapes;
+    ctx->nTiles += n_tiles;
+    ctx->nColumns += columns_allocated;
+    markFirstKernel(ctx);
+    GUDNI_TRY(gudni_launch::rasterTiles(ctx, makeParams(ctx), tileBase, n_tiles));
+    ctx->rasteredTiles = ctx->nTiles;
+    return GUDNI_OK;
+}
+
+static int rasterSceneCommon(gudni_ctx* ctx, const void* devEntries, int n_entries) {
+    GUDNI_TRY(ensureFrameBuffer(ctx));
+    markFirstKernel(ctx);
+    GUDNI_TRY(gudni_bin::binScene(ctx, static_cast<const gudni_shape_entry*>(devEntries), n_entries));
+    GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evBinDone, ctx->stream));
+    GUDNI_TRY(ensureDebug(ctx, 0, ctx->nColumns));
+    GUDNI_TRY(gudni_launch::rasterTiles(ctx, makeParams(ctx), 0, (int)ctx->nTiles));
+    ctx->rasteredTiles = ctx->nTiles;
+    return GUDNI_OK;
+}
+
+// buildTileTree/addShapeToTree + buildRasterJobs + the job loop of queueRasterJobs
+int gudni_b200_raster_scene(gudni_ctx* ctx, const gudni_shape_entry* entries, int n_entries) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if (!ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_scene outside a frame");
+    if (ctx->nTiles) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_scene after other raster calls of the frame");
+    if (n_entries < 0 || (n_entries && !entries)) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_scene: bad entries");
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_TRY(uploadTo(ctx, ctx->entries, entries, (size_t)n_entries * sizeof(gudni_shape_entry)));
+    return rasterSceneCommon(ctx, ctx->entries.ptr, n_entries);
+}
+
+int gudni_b200_raster_scene_device(gudni_ctx* ctx, const void* dev_entries, int n_entries) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if (!ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_scene outside a frame");
+    if (ctx->nTiles) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_scene after other raster calls of the frame");
+    if (n_entries < 0 || (n_entries && !dev_entries)) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_scene: bad entries");
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return rasterSceneCommon(ctx, dev_entries, n_entries);
+}
+
+// OutputPtr read-back, OpenCL/Instances.hs:60-75
+int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if (!ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "frame_end outside a frame");
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_TRY(ensureFrameBuffer(ctx));
+    if (ctx->nTiles) {
+        GUDNI_TRY(gudni_launch::rasterSpill(ctx, makeParams(ctx)));
+    } else {
+        markFirstKernel(ctx);
+    }
+    GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evRasterDone, ctx->stream));
+    const size_t rows = (size_t)(ctx->rowEnd - ctx->rowBegin);
+    if (out_bgra) {
+        const uint32_t* src = ctx->externalTarget
+                                  ? static_cast<const uint32_t*>(ctx->externalTarget) + (size_t)ctx->rowBegin * ctx->width
+                                  : ctx->frame.as<uint32_t>();
+        GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(out_bgra, src, rows * ctx->width * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evDownloadDone, ctx->stream));
+    unsigned long long counters[8] = {0};
+    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(counters, ctx->counters.ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->inFrame = false;
+    gudni_stats s{};
+    s.n_tiles = ctx->nTiles;
+    s.n_shape_refs = ctx->nShapes;
+    s.n_thresholds = (int64_t)counters[gudni_dev::kCntThresholds];
+    s.n_spilled_threads = (int64_t)counters[gudni_dev::kCntSpilled];
+    int64_t dropped = std::max<int64_t>(0, s.n_spilled_threads - ctx->spillCapacity);
+    s.n_overflow_threads = (int64_t)counters[gudni_dev::kCntOverflow] + dropped;
+    s.algorithmic_bytes = (int64_t)ctx->geometryBytes + 16 * ctx->nShapes + 32 * ctx->nTiles + 16 * (int64_t)ctx->nSubstances +
+                          24 * (int64_t)ctx->nPictureUses + (int64_t)ctx->pictureBytes + 4 * (int64_t)ctx->width * (int64_t)rows;
+    cudaEventElapsedTime(&s.ms_upload, ctx->evFrameBegin, ctx->evUploadDone);
+    cudaEventElapsedTime(&s.ms_raster, ctx->evFirstKernel, ctx->evRasterDone);
+    cudaEventElapsedTime(&s.ms_download, ctx->evRasterDone, ctx->evDownloadDone);
+    s.ms_bin = 0.f;
+    if (ctx->binUsed) {
+        cudaEventElapsedTime(&s.ms_bin, ctx->evFirstKernel, ctx->evBinDone);
+        s.ms_raster -= s.ms_bin;
+    }
+    ctx->lastFrameMs = s.ms_raster + s.ms_bin;
+    ctx->lastStats = s;
+    if (stats) *stats = s;
+    return GUDNI_OK;
+}
+
+int gudni_b200_frame_device_ptr(gudni_ctx* ctx, void** dev_bgra, size_t* n_bytes) {
+    if (!ctx || !dev_bgra) return GUDNI_ERR_ARGUMENT;
+    if (ctx->width <= 0) return ctxFail(ctx, GUDNI_ERR_STATE, "no frame yet");
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_TRY(ensureFrameBuffer(ctx));
+    *dev_bgra = ctx->externalTarget ? ctx->externalTarget : ctx->frame.ptr;
+    if (n_bytes) *n_bytes = (size_t)ctx->width * (size_t)(ctx->rowEnd - ctx->rowBegin) * 4;
+    return GUDNI_OK;
+}
+
+int gudni_b200_frame_target(gudni_ctx* ctx, void* dev_canvas_bgra) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if (ctx->nTiles && ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "frame_target after raster calls");
+    ctx->externalTarget = dev_canvas_bgra;
+    return GUDNI_OK;
+}
+
+int gudni_b200_ipc_export_frame(gudni_ctx* ctx, void* handle_64b) {
+    if (!ctx || !handle_64b) return GUDNI_ERR_ARGUMENT;
+    if (!ctx->frame.ptr) return ctxFail(ctx, GUDNI_ERR_STATE, "no frame buffer to export");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    GUDNI_CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, ctx->frame.ptr));
+    std::memcpy(handle_64b, &h, 64);
+    return GUDNI_OK;
+}
+int gudni_b200_ipc_open(gudni_ctx* ctx, const void* handle_64b, void** dev_ptr) {
+    if (!ctx || !handle_64b || !dev_ptr) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle_64b, 64);
+    GUDNI_CUDA_TRY(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GUDNI_OK;
+}
+int gudni_b200_ipc_close(gudni_ctx* ctx, void* dev_ptr) {
+    if (!ctx || !dev_ptr) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    return GUDNI_OK;
+}
+
+int gudni_b200_device_alloc(gudni_ctx* ctx, size_t bytes, void** dev_ptr) {
+    if (!ctx || !dev_ptr) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaMalloc(dev_ptr, std::max<size_t>(bytes, 16)));
+    return GUDNI_OK;
+}
+int gudni_b200_device_free(gudni_ctx* ctx, void* dev_ptr) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaFree(dev_ptr));
+    return GUDNI_OK;
+}
+int gudni_b200_upload(gudni_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes) {
+    if (!ctx || (bytes && (!dev_dst || !host_src))) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return GUDNI_OK;
+}
+int gudni_b200_download(gudni_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+    if (!ctx || (bytes && (!host_dst || !dev_src))) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return GUDNI_OK;
+}
+int gudni_b200_sync(gudni_ctx* ctx) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return GUDNI_OK;
+}
+int gudni_b200_last_frame_ms(gudni_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return GUDNI_ERR_ARGUMENT;
+    *ms = ctx->lastFrameMs;
+    return GUDNI_OK;
+}
+int gudni_b200_launch_count(gudni_ctx* ctx, int64_t* n) {
+    if (!ctx || !n) return GUDNI_ERR_ARGUMENT;
+    *n = ctx->launches;
+    return GUDNI_OK;
+}
+
+int gudni_b200_debug_enable(gudni_ctx* ctx, int on) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    ctx->debug = on != 0;
+    return GUDNI_OK;
+}
+int gudni_b200_debug_thread_counts(gudni_ctx* ctx, int32_t* n_thresholds, int32_t* shape_bits, int64_t capacity,
+                                   int64_t* n_threads) {
+    if (!ctx || !n_threads) return GUDNI_ERR_ARGUMENT;
+    *n_threads = ctx->nColumns;
+    if (!ctx->debug) return ctxFail(ctx, GUDNI_ERR_STATE, "debug taps are not enabled");
+    if (capacity < ctx->nColumns) return GUDNI_OK;   // caller sizes its buffers from *n_threads and calls again
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_thresholds && ctx->nColumns)
+        GUDNI_CUDA_TRY(ctx, cudaMemcpy(n_thresholds, ctx->dbgThresholds.ptr, (size_t)ctx->nColumns * 4, cudaMemcpyDeviceToHost));
+    if (shape_bits && ctx->nColumns)
+        GUDNI_CUDA_TRY(ctx, cudaMemcpy(shape_bits, ctx->dbgShapeBits.ptr, (size_t)ctx->nColumns * 4, cudaMemcpyDeviceToHost));
+    return GUDNI_OK;
+}
+int gudni_b200_debug_binned(gudni_ctx* ctx, gudni_tile* tiles, int64_t tile_capacity, int64_t* n_tiles, gudni_shape* shapes,
+                            int64_t shape_capacity, int64_t* n_shapes) {
+    if (!ctx || !n_tiles || !n_shapes) return GUDNI_ERR_ARGUMENT;
+    *n_tiles = ctx->nTiles;
+    *n_shapes = ctx->nShapes;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (tiles && tile_capacity >= ctx->nTiles && ctx->nTiles)
+        GUDNI_CUDA_TRY(ctx, cudaMemcpy(tiles, ctx->tiles.ptr, (size_t)ctx->nTiles * 32, cudaMemcpyDeviceToHost));
+    if (shapes && shape_capacity >= ctx->nShapes && ctx->nShapes)
+        GUDNI_CUDA_TRY(ctx, cudaMemcpy(shapes, ctx->shapes.ptr, (size_t)ctx->nShapes * 16, cudaMemcpyDeviceToHost));
+    return GUDNI_OK;
+}
+
+}  // extern "C"
