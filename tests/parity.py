@@ -43,3 +43,34 @@ def level1_parity(rasterizer, scene, spec=CANONICAL_SPEC, exact=True):
     assert stats.n_overflow_threads == 0
     assert_images_match(img, ref.image, exact=exact)
     return img, stats, ref
+
+
+def level2_parity(rasterizer, scene, spec=CANONICAL_SPEC, exact=True, ref=None):
+    """Tile binning AND rasterization on the GPU (level 2): tiles, per-tile shape lists, thread
+    counts and pixels against the oracle's tile tree + kernels."""
+    if ref is None:
+        ref = oracle.render(scene, spec, taps=True)
+    assert ref.overflow_threads == 0
+    ref_tiles, ref_shapes = oracle.tiles_in_tree_order(ref.jobs)
+    rasterizer.debug_enable(True)
+    img, stats = rasterizer.raster_scene(0, scene)
+    tiles, shapes = rasterizer.debug_binned()
+    n_thr, bits = rasterizer.debug_thread_counts()
+    rasterizer.debug_enable(False)
+    # tile assignments: boxes, depths, order, column allocations, shape slices — bit-exact
+    assert len(tiles) == len(ref_tiles), (len(tiles), len(ref_tiles))
+    for field in ("left", "top", "right", "bottom", "h_depth", "v_depth", "shape_start", "shape_count"):
+        assert np.array_equal(tiles[field], ref_tiles[field]), field
+    # per-job column allocation as addTileToRasterJob assigns it
+    per_job = np.concatenate([j.tiles["column_allocation"] for j in reversed(ref.jobs)])
+    assert np.array_equal(tiles["column_allocation"], per_job)
+    assert shapes.tobytes() == ref_shapes.tobytes(), "per-tile shape lists differ"
+    # per-thread counts: reorder the oracle's per-job arrays into tree order
+    ref_thr = np.concatenate(list(reversed(ref.n_thresholds)))
+    ref_bits = np.concatenate(list(reversed(ref.shape_bits)))
+    assert np.array_equal(n_thr, ref_thr)
+    assert np.array_equal(bits, ref_bits)
+    assert stats.n_tiles == len(ref_tiles) and stats.n_shape_refs == len(ref_shapes)
+    assert stats.n_thresholds == ref.total_thresholds
+    assert_images_match(img, ref.image, exact=exact)
+    return img, stats, ref
