@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric (BASELINE.json): frames/s of the rasterization hot
+path at 3840x2160 on a synthetic scene of random translucent circles, with the fraction of the
+measured HBM roofline.
+
+  python bench.py --gpus 1 --steps K --warmup W            this repo's CUDA path
+  python bench.py --impl reference --gpus 1 ...            the reference's algorithm on the host
+                                                           cores (restated: oracle/, OpenMP)
+  torchrun ... bench.py --gpus N ...                       N > 1: one 16384^2 canvas partitioned
+                                                           into tile-row strips, one rank per GPU,
+                                                           strips gathered on rank 0 (strong scaling)
+
+A "step" is one frame: tile binning + threshold generation + sort + sweep/compositing, producing
+the BGRA8 bitmap.  `value` times it with the scene resident in HBM and the frame left in HBM;
+`e2e` times the public call a client makes (host buffers in, host bitmap out).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (scene factory name, description)
+    "S4": ("s4", "S4: 100,000 random translucent circles (1.7M quadratic curves), 3840x2160, seed 0x5EED0004"),
+    "S4b": ("s4b", "S4b: 6,250 random translucent circles (100k curves), 3840x2160, seed 0x5EED004B"),
+    "S5": ("s5", "S5: 62,500 random translucent circles r 20-200 (1M curves), 16384x16384, seed 0x5EED0005"),
+    "S5b": ("s5b", "S5b: 1,000,000 random translucent circles r 5-10, 16384x16384, seed 0x5EED005B"),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                parts = [p.strip() for p in out.split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for n, v in zip(names, parts[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_scene(workload):
+    from gudni_b200 import scenes
+    return getattr(scenes, WORKLOADS[workload][0])()
+
+
+def algorithmic_bytes(scene, n_tiles, n_shape_refs, rows=None):
+    """A(frame), SURVEY.md §8(d)."""
+    rows = scene.height if rows is None else rows
+    return (scene.geometry.nbytes + 16 * n_shape_refs + 32 * n_tiles + 16 * len(scene.substances) +
+            24 * len(scene.picture_uses) + scene.picture_bytes.nbytes + 4 * scene.width * rows)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own algorithm (three phases per job over the CPU tile tree) on the
+# host cores.  The reference cannot be built here (Haskell + OpenCL), so this is the
+# restated port in oracle/ with OpenMP over the NDRange.
+# ---------------------------------------------------------------------------------------------------
+def oracle_frame_sampler(scene, budget_s=12.0):
+    """Returns f() -> (seconds per FULL frame, sample description).  Frames that would take longer
+    than `budget_s` are sampled: the tile tree is built for the whole scene, then an evenly spread
+    subset of the jobs is rasterized and the raster time is scaled by jobs_total / jobs_sampled."""
+    from oracle import oracle
+
+    t0 = time.perf_counter()
+    jobs = oracle.build_raster_jobs(scene)
+    t_tree = time.perf_counter() - t0
+    probe = jobs[len(jobs) // 2: len(jobs) // 2 + 1]
+    t0 = time.perf_counter()
+    oracle.raster_jobs(scene, probe, taps=False)
+    t_probe = time.perf_counter() - t0
+    est = t_tree + t_probe * len(jobs)
+    stride = max(1, int(np.ceil(est / budget_s)))
+    picked = jobs[stride // 2::stride] if stride > 1 else jobs
+    desc = (f"tile tree for the whole scene + {len(picked)} of {len(jobs)} raster jobs "
+            f"(every {stride}th job of {scene.name}), raster time scaled by {len(jobs)}/{len(picked)}"
+            if stride > 1 else f"one full frame of {scene.name} (tile tree + {len(jobs)} raster jobs)")
+
+    def run():
+        t0 = time.perf_counter()
+        js = oracle.build_raster_jobs(scene)
+        t1 = time.perf_counter()
+        sel = js[stride // 2::stride] if stride > 1 else js
+        oracle.raster_jobs(scene, sel, taps=False)
+        t2 = time.perf_counter()
+        return (t1 - t0) + (t2 - t1) * len(js) / len(sel)
+
+    return run, desc
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle
+    scene = make_scene(args.workload)
+    # keep the whole --steps/--warmup run within a few minutes on the host cores
+    budget = float(np.clip(150.0 / (args.steps + 1), 2.0, 12.0))
+    run, desc = oracle_frame_sampler(scene, budget_s=budget)
+    for _ in range(min(args.warmup, 1)):
+        run()
+    times = [run() for _ in range(args.steps)]
+    t = float(np.mean(times))
+    cores = oracle.host_threads()
+    value = 1.0 / t
+    line = {
+        "impl": "reference", "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][1], "canvas": [scene.width, scene.height],
+                   "spec": "G=256 MAXT=1024 maxStrandsPerTile=1022 MAXSHAPE=127"},
+        "mpixel_per_s": scene.width * scene.height * value / 1e6,
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
+                         "note": "restated-reference CPU (OpenMP), not PoCL: the Haskell+OpenCL reference cannot "
+                                 "be built in this image"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------------
+def run_native(args, rank, world, local_rank):
+    import torch
+    from gudni_b200.raster import DeviceScene, setup_rasterizer
+    from gudni_b200.strips import StripRenderer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    scene = make_scene(args.workload)
+    r = setup_rasterizer(local_rank)
+    stream = torch.cuda.current_stream()
+    r.set_stream(stream.cuda_stream)
+    strips = StripRenderer(r, scene, rank, world, dist, mode=args.gather)
+    dscene = DeviceScene(r, scene, entries=strips.entries)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, frame left in HBM -----------------------------------------
+    for i in range(args.warmup):
+        strips.render(i, dscene)
+    launches0 = r.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ms, raster_ms, bin_ms = [], [], []
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                      # L2 flush between timed iterations (not timed)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        strips.render(args.warmup + i, dscene)
+        e1.record(stream)
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+        st = getattr(strips, "last_stats", None)
+        if st is not None:
+            raster_ms.append(st.ms_raster)
+            bin_ms.append(st.ms_bin)
+    clocks = sampler.stop()
+    launches = r.launch_count() - launches0
+    t_dev = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms = float(t_dev.item())
+    stats = getattr(strips, "last_stats", None)
+
+    # ---- e2e: the public call with host buffers (pageable, as the Haskell caller has them) --------
+    e2e_times = []
+    h2d = (scene.geometry.nbytes + scene.substances.nbytes + scene.picture_bytes.nbytes + scene.picture_uses.nbytes +
+           strips.entries.nbytes)
+    rows = strips.my_rows[1] - strips.my_rows[0]
+    d2h = 4 * scene.width * (scene.height if world == 1 else 0)
+    host_img = np.empty((scene.height, scene.width), dtype=np.uint32) if rank == 0 else None
+    n_e2e = max(3, min(args.steps, 10))
+    for i in range(2 + n_e2e):
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            r.frame_target(None)
+            r.raster_scene(i, scene, out=host_img)
+        else:
+            canvas = strips.render(i, None)
+            if rank == 0:
+                host_img[...] = canvas.cpu().numpy().view(np.uint32)
+                d2h = 4 * scene.width * scene.height
+        barrier()
+        if i >= 2:
+            e2e_times.append(time.perf_counter() - t0)
+    t_e2e = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        ms_per_step = total_ms / args.steps
+        value = 1e3 / ms_per_step
+        a_bytes = stats.algorithmic_bytes if stats is not None else 0
+        k_ms = float(np.mean(raster_ms)) if raster_ms else ms_per_step
+        achieved = a_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(args.workload)
+        line = {
+            "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload][1], "canvas": [scene.width, scene.height],
+                       "spec": "G=256 MAXT=1024 maxStrandsPerTile=1022 MAXSHAPE=127",
+                       "l2": "flushed between timed iterations (256 MiB write)",
+                       "parallelism": "1 GPU, whole frame" if world == 1 else
+                       f"{world} tile-row strips, gather={args.gather}",
+                       "strips": strips.rows if world > 1 else None},
+            "mpixel_per_s": scene.width * scene.height * value / 1e6,
+            "clocks": clocks,
+            "e2e": {"value": 1.0 / float(t_e2e.item()), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "raster_tiles_kernel (+ raster_spill_kernel)", "kernel_ms": k_ms,
+                         "bin_ms": float(np.mean(bin_ms)) if bin_ms else None, "algorithmic_bytes": int(a_bytes)},
+            "frame": stats.as_dict() if stats is not None else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            run, desc = oracle_frame_sampler(scene, budget_s=10.0)
+            t = float(np.mean([run() for _ in range(2)]))
+            from oracle import oracle
+            line["cpu_baseline"] = {"value": 1.0 / t, "unit": "frames/s", "cores": oracle.host_threads(),
+                                    "kind": "port", "sample": desc}
+        print(json.dumps(line), flush=True)
+    strips.close()
+    dscene.free()
+    r.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        # the metric is quoted on the 4K scene; a frame that fits one GPU is not sharded
+        # (BASELINE.json north_star), so N > 1 runs the 16K^2 canvas the strips exist for
+        args.workload = "S4" if max(world, args.gpus) == 1 else "S5"
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,8 @@ struct gudni_ctx {
     int device = 0;
     gudni_spec spec{};
     int computeDepth = 8;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream in use (own or caller's)
+    cudaStream_t ownStream = nullptr;
     cudaStream_t copyStream = nullptr;
     std::string err;
     int64_t launches = 0;
@@ -47,6 +48,7 @@ struct gudni_ctx {
     // output
     DevBuf frame;
     void* externalTarget = nullptr;   // gudni_b200_frame_target
+    int externalRowOrigin = 0;
 
     // counters / spill
     DevBuf counters;        // 8 x u64

@@ -30,7 +30,7 @@ FrameParams makeParams(gudni_ctx* ctx) {
     P.pictureUses = static_cast<const gudni_picture_use*>(ctx->pictureUsesPtr);
     if (ctx->externalTarget) {
         P.out = static_cast<uint32_t*>(ctx->externalTarget);
-        P.rowOrigin = 0;
+        P.rowOrigin = ctx->externalRowOrigin;
     } else {
         P.out = ctx->frame.as<uint32_t>();
         P.rowOrigin = ctx->rowBegin;
@@ -130,7 +130,8 @@ int gudni_b200_init(int device, const gudni_spec* want, gudni_spec* got, gudni_c
     if (got) *got = spec;
     auto fail = [&](int code) { gudni_b200_destroy(ctx); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
+    ctx->stream = ctx->ownStream;
     if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
     cudaEvent_t* evs[] = {&ctx->evFrameBegin, &ctx->evUploadDone, &ctx->evBinDone, &ctx->evRasterDone,
                           &ctx->evDownloadDone, &ctx->evFirstKernel};
@@ -162,7 +163,7 @@ void gudni_b200_destroy(gudni_ctx* ctx) {
                          ctx->evFirstKernel};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     delete ctx;
 }
@@ -324,7 +325,8 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     const size_t rows = (size_t)(ctx->rowEnd - ctx->rowBegin);
     if (out_bgra) {
         const uint32_t* src = ctx->externalTarget
-                                  ? static_cast<const uint32_t*>(ctx->externalTarget) + (size_t)ctx->rowBegin * ctx->width
+                                  ? static_cast<const uint32_t*>(ctx->externalTarget) +
+                                        (size_t)(ctx->rowBegin - ctx->externalRowOrigin) * ctx->width
                                   : ctx->frame.as<uint32_t>();
         GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(out_bgra, src, rows * ctx->width * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -366,10 +368,21 @@ int gudni_b200_frame_device_ptr(gudni_ctx* ctx, void** dev_bgra, size_t* n_bytes
     return GUDNI_OK;
 }
 
-int gudni_b200_frame_target(gudni_ctx* ctx, void* dev_canvas_bgra) {
+int gudni_b200_frame_target(gudni_ctx* ctx, void* dev_bgra, int row_origin) {
     if (!ctx) return GUDNI_ERR_ARGUMENT;
     if (ctx->nTiles && ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "frame_target after raster calls");
-    ctx->externalTarget = dev_canvas_bgra;
+    if (row_origin < 0) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "frame_target: negative row origin");
+    ctx->externalTarget = dev_bgra;
+    ctx->externalRowOrigin = dev_bgra ? row_origin : 0;
+    return GUDNI_OK;
+}
+
+int gudni_b200_set_stream(gudni_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if (ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "set_stream inside a frame");
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->ownStream;
     return GUDNI_OK;
 }
 

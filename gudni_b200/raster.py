@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "gudni_b200_ipc_export_frame", "gudni_b200_ipc_open", "gudni_b200_ipc_close", "gudni_b200_device_alloc",
     "gudni_b200_device_free", "gudni_b200_upload", "gudni_b200_download", "gudni_b200_frame_begin_device",
     "gudni_b200_raster_scene_device", "gudni_b200_sync", "gudni_b200_last_frame_ms", "gudni_b200_launch_count",
-    "gudni_b200_debug_enable", "gudni_b200_debug_thread_counts", "gudni_b200_debug_binned",
+    "gudni_b200_set_stream", "gudni_b200_debug_enable", "gudni_b200_debug_thread_counts", "gudni_b200_debug_binned",
     "gudni_b200_last_error", "gudni_b200_destroy",
 ]
 
@@ -61,7 +61,8 @@ def load_library():
     L.gudni_b200_raster_scene_device.argtypes = [vp, vp, i32]
     L.gudni_b200_frame_end.argtypes = [vp, vp, c.POINTER(CStats)]
     L.gudni_b200_frame_device_ptr.argtypes = [vp, c.POINTER(vp), c.POINTER(sz)]
-    L.gudni_b200_frame_target.argtypes = [vp, vp]
+    L.gudni_b200_frame_target.argtypes = [vp, vp, i32]
+    L.gudni_b200_set_stream.argtypes = [vp, vp]
     L.gudni_b200_ipc_export_frame.argtypes = [vp, vp]
     L.gudni_b200_ipc_open.argtypes = [vp, vp, c.POINTER(vp)]
     L.gudni_b200_ipc_close.argtypes = [vp, vp]
@@ -99,15 +100,17 @@ class FrameStats:
 class DeviceScene:
     """Frame inputs resident in HBM (bench.py's inputs-in-HBM leg)."""
 
-    def __init__(self, rasterizer, scene):
+    def __init__(self, rasterizer, scene, entries=None):
         self.r = rasterizer
         self.scene = scene
         self._bufs = []
+        entries = scene.entries if entries is None else entries
+        self.n_entries = len(entries)
         self.geometry = self._put(scene.geometry)
         self.substances = self._put(np.ascontiguousarray(scene.substances, np.float32))
         self.pictures = self._put(scene.picture_bytes)
         self.picture_uses = self._put(scene.picture_uses)
-        self.entries = self._put(scene.entries)
+        self.entries = self._put(entries)
 
     def _put(self, arr):
         arr = np.ascontiguousarray(arr)
@@ -229,8 +232,13 @@ class Rasterizer:
         self._check(self._L.gudni_b200_frame_device_ptr(self._ctx, ctypes.byref(p), ctypes.byref(n)))
         return p.value, n.value
 
-    def frame_target(self, dev_ptr):
-        self._check(self._L.gudni_b200_frame_target(self._ctx, ctypes.c_void_p(dev_ptr) if dev_ptr else None))
+    def frame_target(self, dev_ptr, row_origin=0):
+        self._check(self._L.gudni_b200_frame_target(self._ctx, ctypes.c_void_p(dev_ptr) if dev_ptr else None,
+                                                    row_origin))
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        self._check(self._L.gudni_b200_set_stream(self._ctx, ctypes.c_void_p(cuda_stream) if cuda_stream else None))
 
     def sync(self):
         self._check(self._L.gudni_b200_sync(self._ctx))

@@ -1,0 +1,143 @@
+"""Multi-GPU strip partition: one process per GPU, each rank bins and rasterizes
+a contiguous run of root-tile rows; the finished strips are gathered on the presenting rank.
+
+The reference has no counterpart (one OpenCLState = one device, OpenCL/Setup.hs:118-120).  Tiles and
+columns are independent, so the path shards with no data-path exchange except the final gather of
+pixels.  Two gather modes:
+
+  "nccl"  every rank renders into its own strip tensor; non-presenting ranks `isend` it, the
+          presenting rank `irecv`s straight into the row slice of the canvas (NCCL over NVLink).
+  "p2p"   the presenting rank's canvas is mapped into every process with CUDA IPC and the raster
+          kernel stores its pixels there directly, so the transfer overlaps the rasterization and
+          no separate gather pass exists; a barrier closes the frame.
+"""
+import numpy as np
+
+
+def partition_rows(scene, n_ranks, tile_rows=256):
+    """Contiguous runs of root-tile rows per rank, balanced by a cheap work estimate: shape-box
+    area clipped to each tile row plus the row's pixel count (covers empty rows)."""
+    n_rows = (scene.height + tile_rows - 1) // tile_rows
+    e = scene.entries
+    weight = np.zeros(n_rows, dtype=np.float64)
+    if len(e):
+        top = np.clip(e["top"].astype(np.float64), 0, scene.height)
+        bottom = np.clip(e["bottom"].astype(np.float64), 0, scene.height)
+        width = np.clip(e["right"], 0, scene.width).astype(np.float64) - np.clip(e["left"], 0, scene.width)
+        for r in range(n_rows):
+            y0, y1 = r * tile_rows, min((r + 1) * tile_rows, scene.height)
+            weight[r] = float((np.clip(np.minimum(bottom, y1) - np.maximum(top, y0), 0, None) * width).sum())
+    weight += float(scene.width) * tile_rows * 0.5
+    n_ranks = min(n_ranks, n_rows)
+    cum = np.concatenate([[0.0], np.cumsum(weight)])
+    bounds = [0]
+    for k in range(1, n_ranks):
+        target = cum[-1] * k / n_ranks
+        idx = int(np.searchsorted(cum, target))
+        idx = max(bounds[-1] + 1, min(idx, n_rows - (n_ranks - k)))
+        bounds.append(idx)
+    bounds.append(n_rows)
+    return [(bounds[k] * tile_rows, min(bounds[k + 1] * tile_rows, scene.height)) for k in range(n_ranks)]
+
+
+class StripRenderer:
+    """Per-rank driver.  `dist` is torch.distributed (already initialised) or None for one GPU."""
+
+    def __init__(self, rasterizer, scene, rank=0, world=1, dist=None, mode="nccl", presenting_rank=0):
+        import torch
+        self.torch = torch
+        self.r, self.scene, self.rank, self.world, self.dist = rasterizer, scene, rank, world, dist
+        self.mode = mode if world > 1 else "local"
+        self.presenting = presenting_rank
+        self.rows = partition_rows(scene, world, rasterizer.spec.max_tile_size)
+        while len(self.rows) < world:
+            self.rows.append((scene.height, scene.height))   # more ranks than tile rows: idle ranks
+        self.my_rows = self.rows[rank]
+        self.entries = scene.subset_rows(*self.my_rows) if self.my_rows[1] > self.my_rows[0] else scene.entries[:0]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.canvas = None
+        self.strip = None
+        self._peer_canvas = None
+        h, w = scene.height, scene.width
+        if rank == presenting_rank:
+            self.canvas = torch.empty((h, w), dtype=torch.int32, device=dev)
+        if self.mode == "p2p":
+            self._setup_p2p(dev)
+        elif rank != presenting_rank:
+            rows = self.my_rows[1] - self.my_rows[0]
+            self.strip = torch.empty((max(rows, 1), w), dtype=torch.int32, device=dev)
+
+    # -- CUDA IPC: map the presenting rank's canvas into this process --------------------------------
+    def _setup_p2p(self, dev):
+        import ctypes
+        torch, dist = self.torch, self.dist
+        handle = torch.zeros(64, dtype=torch.uint8)
+        if self.rank == self.presenting:
+            h = (ctypes.c_ubyte * 64)()
+            # export the torch-owned canvas through the runtime directly (cudaIpcGetMemHandle)
+            rt = ctypes.CDLL("libcudart.so.12")
+            rc = rt.cudaIpcGetMemHandle(ctypes.byref(h), ctypes.c_void_p(self.canvas.data_ptr()))
+            if rc != 0:
+                raise RuntimeError(f"cudaIpcGetMemHandle failed: {rc}")
+            handle = torch.frombuffer(bytearray(h), dtype=torch.uint8).clone()
+        hd = handle.to(dev)
+        dist.broadcast(hd, src=self.presenting)
+        if self.rank != self.presenting:
+            raw = bytes(hd.cpu().numpy().tobytes())
+            p = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(raw)
+            self.r._check(self.r._L.gudni_b200_ipc_open(self.r._ctx, buf, ctypes.byref(p)))
+            self._peer_canvas = p.value
+
+    def close(self):
+        if self._peer_canvas:
+            import ctypes
+            self.r._L.gudni_b200_ipc_close(self.r._ctx, ctypes.c_void_p(self._peer_canvas))
+            self._peer_canvas = None
+        self.r.frame_target(None)
+
+    # -- one frame ---------------------------------------------------------------------------------
+    def render(self, frame=0, dscene=None):
+        """Rasterize this rank's strip and gather.  Returns the canvas tensor on the presenting rank."""
+        r, torch = self.r, self.torch
+        rows = self.my_rows
+        active = rows[1] > rows[0]
+        if self.rank == self.presenting:
+            r.frame_target(self.canvas.data_ptr(), 0)
+        elif self.mode == "p2p":
+            r.frame_target(self._peer_canvas, 0)
+        else:
+            r.frame_target(self.strip.data_ptr(), rows[0])
+        if active:
+            if dscene is not None:
+                r.frame_begin_device(dscene, frame)
+            else:
+                r.frame_begin(self.scene, frame)
+            if self.world > 1:
+                r.frame_strip(*rows)
+            if dscene is not None:
+                r.raster_entries_device(dscene.entries, dscene.n_entries)
+            else:
+                r.raster_entries(self.entries)
+            _, self.last_stats = r.frame_end(want_image=False)
+        if self.world > 1:
+            self._gather()
+        return self.canvas
+
+    def _gather(self):
+        dist, torch = self.dist, self.torch
+        if self.mode == "p2p":
+            torch.cuda.synchronize()
+            dist.barrier()
+            return
+        ops = []
+        if self.rank == self.presenting:
+            for k, (y0, y1) in enumerate(self.rows):
+                if k != self.rank and y1 > y0:
+                    ops.append(dist.P2POp(dist.irecv, self.canvas[y0:y1], k))
+        elif self.my_rows[1] > self.my_rows[0]:
+            n = self.my_rows[1] - self.my_rows[0]
+            ops.append(dist.P2POp(dist.isend, self.strip[:n], self.presenting))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()

@@ -1,0 +1,49 @@
+{-# LANGUAGE ForeignFunctionInterface #-}
+-- | Raw bindings to libgudni_b200.so (include/gudni_b200.h).  SOURCE ONLY: GHC is not available
+-- in the build image, so this module has not been compiled; it shows the binding a Gudni
+-- maintainer adds next to the existing direct FFI in Graphics.Gudni.Interface.GLInterop
+-- (src/Graphics/Gudni/Interface/GLInterop.hs:60-113).
+module Graphics.Gudni.CUDA.FFI where
+
+import Foreign.C.Types
+import Foreign.C.String (CString)
+import Foreign.Ptr
+import Data.Word
+
+-- | Opaque gudni_ctx.
+data GudniCtx
+
+-- | gudni_spec = RasterSpec (OpenCL/Rasterizer.hs:37-50), six CInts in declaration order.
+-- | gudni_stats: see include/gudni_b200.h; Storable instances live in Graphics.Gudni.CUDA.Setup.
+
+foreign import ccall safe "gudni_b200_init"
+  c_init :: CInt -> Ptr CInt {- want spec or nullPtr -} -> Ptr CInt {- got spec -} -> Ptr (Ptr GudniCtx) -> IO CInt
+
+foreign import ccall safe "gudni_b200_frame_begin"
+  c_frameBegin :: Ptr GudniCtx
+               -> Ptr CChar -> CSize            -- geoGeometryPile bytes (Raster/Serialize.hs:111)
+               -> Ptr CFloat -> CInt            -- suSubstancePile (Raster/Serialize.hs:195)
+               -> Ptr Word8 -> CSize            -- picture heap (Figure/Picture.hs:159)
+               -> Ptr () -> CInt                -- picture usages, 24 bytes each
+               -> Ptr CFloat                    -- suBackgroundColor r g b a
+               -> CInt -> CInt -> CInt          -- bitmap width, height, frame count
+               -> IO CInt
+
+foreign import ccall safe "gudni_b200_raster_job"
+  c_rasterJob :: Ptr GudniCtx
+              -> Ptr () -> CInt                 -- rJShapePile (16 bytes each)
+              -> Ptr () -> CInt                 -- rJTilePile  (32 bytes each)
+              -> CInt -> CInt                   -- rJColumnAllocation, jobIndex
+              -> IO CInt
+
+foreign import ccall safe "gudni_b200_raster_scene"
+  c_rasterScene :: Ptr GudniCtx -> Ptr () -> CInt -> IO CInt   -- un-binned shape entries (32 bytes each)
+
+foreign import ccall safe "gudni_b200_frame_end"
+  c_frameEnd :: Ptr GudniCtx -> Ptr CUInt {- HostBitmapTarget pointer, DrawTarget.hs:34 -} -> Ptr () -> IO CInt
+
+foreign import ccall safe "gudni_b200_last_error"
+  c_lastError :: Ptr GudniCtx -> IO CString
+
+foreign import ccall safe "gudni_b200_destroy"
+  c_destroy :: Ptr GudniCtx -> IO ()

@@ -156,11 +156,16 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
 /* Device-side access for callers that keep data on the GPU (bench, multi-GPU gather).  The frame
  * pointer stays valid until the next frame_begin with a different size, or destroy. */
 int gudni_b200_frame_device_ptr(gudni_ctx* ctx, void** dev_bgra, size_t* n_bytes);
-/* Redirect pixel stores of this context to a caller-owned device buffer holding the full canvas
- * (width*height words; row y of the canvas at word y*width) — e.g. a peer GPU's frame mapped
- * through CUDA IPC, so strips land on the presenting GPU over NVLink without a separate gather.
- * NULL restores the context's own frame buffer. */
-int gudni_b200_frame_target(gudni_ctx* ctx, void* dev_canvas_bgra);
+/* Redirect pixel stores of this context to a caller-owned device buffer whose first row is canvas
+ * row `row_origin` (row y of the canvas at word (y - row_origin)*width).  Two uses: a torch-owned
+ * strip tensor (row_origin = the strip's first row), or a peer GPU's full canvas mapped through
+ * CUDA IPC (row_origin = 0), so strips land on the presenting GPU over NVLink without a separate
+ * gather.  NULL restores the context's own frame buffer. */
+int gudni_b200_frame_target(gudni_ctx* ctx, void* dev_bgra, int row_origin);
+/* Run this context's work on a caller-owned CUDA stream (a cudaStream_t passed as void*), e.g.
+ * torch's current stream so the caller's events bracket the kernels.  NULL restores the context's
+ * own stream. */
+int gudni_b200_set_stream(gudni_ctx* ctx, void* cuda_stream);
 /* CUDA-IPC plumbing for the above (one process per GPU). `handle` is 64 bytes. */
 int gudni_b200_ipc_export_frame(gudni_ctx* ctx, void* handle_64b);
 int gudni_b200_ipc_open(gudni_ctx* ctx, const void* handle_64b, void** dev_ptr);
