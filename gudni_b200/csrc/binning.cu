@@ -68,7 +68,7 @@ struct BinParams {
     gudni_shape* shapes;
     int32_t* tileThreadBase;
 };
-enum { kArenaCursor = 0, kOverflow = 1, kTotalTiles = 2, kTotalRefs = 3 };
+enum { kArenaCursor = 0, kOverflow = 1, kTotalTiles = 2, kTotalRefs = 3, kTooManyShapes = 4 };
 
 // y-major Morton rank of a root tile: traverseTileTree visits top before bottom, then left before right
 __host__ __device__ inline uint32_t mortonYX(uint32_t tx, uint32_t ty) {
@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(256) bin_emit(const BinParams P) {
         const uint32_t tileIdx = tileBase + i;
         const uint32_t shapeStart = shapeBase + n.outStart;
         if (lane == 0) {
+            if (n.count > 65535u) P.counters[kTooManyShapes] = 1ull;   // the raster kernels index a tile's list with 16 bits
             gudni_tile t;
             t.left = originXOf(P, rtx) + n.x;
             t.top = originYOf(P, rty) + n.y;

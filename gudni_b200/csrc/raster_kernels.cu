@@ -12,11 +12,14 @@ template <int CAP>
 __global__ void __launch_bounds__(1024) raster_tiles_kernel(const FrameParams P, int tileBase) {
     __shared__ unsigned long long sThresholds;
     __shared__ gudni_tile sTile;
+    __shared__ TileTable sTable;
     const int tileIndex = tileBase + blockIdx.x;
     if (threadIdx.x == 0) {
         sThresholds = 0ull;
         sTile = P.tiles[tileIndex];
     }
+    __syncthreads();
+    fillTileTable(P, sTable, sTile.shape_start, sTile.shape_count);
     __syncthreads();
     const int column = threadIdx.x;
     const ThreadGeom g = threadGeom(P, sTile, column);
@@ -24,7 +27,7 @@ __global__ void __launch_bounds__(1024) raster_tiles_kernel(const FrameParams P,
         ChipQueue<CAP> q;
         const int threadId = P.tileThreadBase[tileIndex] + column;
         int generated;
-        bool ok = rasterThread(P, g, q, threadId, generated);
+        bool ok = rasterThread(P, sTable, min(sTile.shape_count, (uint32_t)kTileTableCap), g, q, threadId, generated);
         if (ok) {
             atomicAdd(&sThresholds, (unsigned long long)generated);
         } else {
@@ -41,6 +44,9 @@ __global__ void __launch_bounds__(1024) raster_tiles_kernel(const FrameParams P,
 // spill list with a grid stride, so the scratch footprint is fixed (slots x MAXTHRESHOLDS x 20 B)
 // regardless of how many threads spilled.
 __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, float4* thr, uint32_t* hdr, int slots) {
+    // spilled threads come from arbitrary tiles: the table is empty (count 0) and every layer
+    // takes the global-memory path
+    __shared__ TileTable sTable;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long n = P.counters[kCntSpilled];
     if (n > (unsigned long long)P.spillCapacity) n = (unsigned long long)P.spillCapacity;
@@ -56,7 +62,7 @@ __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, 
         q.cap = P.maxThresholds;
         // the first kernel does not count the thresholds of a thread it hands over
         int generated;
-        bool ok = rasterThread(P, g, q, P.tileThreadBase[tileIndex] + column, generated);
+        bool ok = rasterThread(P, sTable, 0u, g, q, P.tileThreadBase[tileIndex] + column, generated);
         if (generated > 0) atomicAdd(&P.counters[kCntThresholds], (unsigned long long)generated);
         if (!ok) atomicAdd(&P.counters[kCntOverflow], 1ull);
     }

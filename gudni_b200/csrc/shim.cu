@@ -179,6 +179,7 @@ int gudni_b200_frame_begin(gudni_ctx* ctx, const void* geometry, size_t geometry
     if ((geometry_bytes && !geometry) || (n_substances && !substances) || (n_picture_bytes && !picture_bytes) ||
         (n_picture_uses && !picture_uses) || !background_rgba || n_substances < 0 || n_picture_uses < 0)
         return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "frame_begin: null or negative-sized input");
+    if (n_substances >= (1 << 30)) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "frame_begin: more than 2^30 substances");
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evFrameBegin, ctx->stream));
     GUDNI_TRY(beginFrameCommon(ctx, background_rgba, width, height, frame_number));
@@ -252,6 +253,8 @@ int gudni_b200_raster_job(gudni_ctx* ctx, const gudni_shape* shapes, int n_shape
             return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_job: tile %d shape slice out of range", i);
         if (ti.column_allocation < 0 || (int64_t)ti.column_allocation + G > (int64_t)columns_allocated)
             return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_job: tile %d column allocation out of range", i);
+        if (ti.shape_count > 65535u)
+            return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_job: tile %d lists more than 65535 shapes", i);
         if (ti.h_depth < 0 || ti.h_depth > 15 || ti.v_depth < 0 || ti.v_depth > 15)
             return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_job: tile %d depth out of range", i);
         t[i].shape_start = ti.shape_start + (uint32_t)ctx->nShapes;
@@ -333,8 +336,13 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evDownloadDone, ctx->stream));
     unsigned long long counters[8] = {0};
     GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(counters, ctx->counters.ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long binCounters[8] = {0};
+    if (ctx->binUsed)
+        GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(binCounters, ctx->binCounters.ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->inFrame = false;
+    if (binCounters[4])
+        return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "a minimum-size tile lists more than 65535 shapes: unsupported by the raster kernels");
     gudni_stats s{};
     s.n_tiles = ctx->nTiles;
     s.n_shape_refs = ctx->nShapes;
