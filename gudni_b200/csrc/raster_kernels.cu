@@ -2,42 +2,63 @@
 // of spilled threads) and their launch wrappers.  Device arithmetic is in raster_device.cuh.
 #include "raster_kernels.cuh"
 
+#include <algorithm>
+
+#include "raster_warp.cuh"
+
 using namespace gudni_dev;
 
-// Fused generate -> sort -> sweep: one CTA per tile, one thread per (column, slab) exactly as the
-// reference's NDRange `Work2D numTiles threadsPerTile` with work-group [1, threadsPerTile]
-// (OpenCL/CallKernels.hs:141-142), but a single launch covers every tile of the frame and the
-// three phases never leave the SM.
-template <int CAP>
-__global__ void __launch_bounds__(1024) raster_tiles_kernel(const FrameParams P, int tileBase) {
-    __shared__ unsigned long long sThresholds;
-    __shared__ gudni_tile sTile;
-    __shared__ TileTable sTable;
-    const int tileIndex = tileBase + blockIdx.x;
-    if (threadIdx.x == 0) {
-        sThresholds = 0ull;
-        sTile = P.tiles[tileIndex];
-    }
-    __syncthreads();
-    fillTileTable(P, sTable, sTile.shape_start, sTile.shape_count);
-    __syncthreads();
-    const int column = threadIdx.x;
-    const ThreadGeom g = threadGeom(P, sTile, column);
-    if (g.active) {
-        ChipQueue<CAP> q;
-        const int threadId = P.tileThreadBase[tileIndex] + column;
-        int generated;
-        bool ok = rasterThread(P, sTable, min(sTile.shape_count, (uint32_t)kTileTableCap), g, q, threadId, generated);
-        if (ok) {
-            atomicAdd(&sThresholds, (unsigned long long)generated);
+constexpr int kWarpsPerCta = 4;
+
+// Fused generate -> sort -> sweep, persistent: the grid is sized to what the chip holds resident and
+// every warp pulls (tile, 32-column group) units from a global counter until the frame is done, so
+// a warp that draws a cheap unit moves on instead of waiting at a CTA barrier for the slowest warp
+// of its tile, and the tail of the frame is spread over all SMs.  The unit is the reference's
+// work-group sliced by warps: `Work2D numTiles threadsPerTile` (OpenCL/CallKernels.hs:141-142).
+__global__ void __launch_bounds__(kWarpsPerCta * 32) raster_warps_kernel(const FrameParams P, int tileBase, int nTiles,
+                                                                         unsigned int* workCounter) {
+    __shared__ WarpScratch scratch[kWarpsPerCta];
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpScratch& W = scratch[warp];
+    const int warpShift = P.computeDepth - 5;                    // warps per tile = threadsPerTile / 32
+    const unsigned totalUnits = (unsigned)nTiles << warpShift;
+    const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
+    for (;;) {
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd(workCounter, 1u);
+        unit = __shfl_sync(full, unit, 0);
+        if (unit >= totalUnits) break;
+        const int tileIndex = tileBase + (int)(unit >> warpShift);
+        const int column = (int)((unit & ((1u << warpShift) - 1u)) << 5) + lane;
+        const gudni_tile tile = P.tiles[tileIndex];
+        int generated = -1;
+        int failed = 0;
+        if (tile.shape_count <= denseCap) {
+            failed = rasterWarpDense<ChipQueue<kChipQueueCapacity>>(P, W, tile, tileIndex, column, generated);
         } else {
+            // a tile that stopped splitting at the 8-pixel floor with more shapes than stack bits:
+            // lane-private sweep with the bit -> shape table, colours through global memory
+            const ThreadGeom g = threadGeom(P, tile, column);
+            if (g.active) {
+                ChipQueue<kChipQueueCapacity> q;
+                const bool ok = rasterThread(P, *reinterpret_cast<const TileTable*>(&W), 0u, g, q,
+                                             P.tileThreadBase[tileIndex] + column, generated);
+                failed = ok ? 0 : 1;
+            }
+        }
+        __syncwarp();
+        // statistics: thresholds of lanes that completed here (spilled lanes are counted by the replay)
+        unsigned int mine = (!failed && generated > 0) ? (unsigned)generated : 0u;
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(full, mine, d);
+        if (lane == 0 && mine) atomicAdd(&P.counters[kCntThresholds], (unsigned long long)mine);
+        if (failed) {
             // replayed by raster_spill_kernel against an HBM queue of MAXTHRESHOLDS entries
-            unsigned long long slot = atomicAdd(&P.counters[kCntSpilled], 1ull);
-            if (slot < (unsigned long long)P.spillCapacity) P.spillList[slot] = ((unsigned long long)tileIndex << 32) | (unsigned long long)column;
+            const unsigned long long slot = atomicAdd(&P.counters[kCntSpilled], 1ull);
+            if (slot < (unsigned long long)P.spillCapacity)
+                P.spillList[slot] = ((unsigned long long)tileIndex << 32) | (unsigned long long)column;
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && sThresholds) atomicAdd(&P.counters[kCntThresholds], sThresholds);
 }
 
 // Replay of spilled column-threads.  Persistent: each thread owns one HBM queue slot and walks the
@@ -72,8 +93,17 @@ namespace gudni_launch {
 
 int rasterTiles(gudni_ctx* ctx, const FrameParams& P, int tileBase, int nTiles) {
     if (nTiles <= 0) return GUDNI_OK;
-    const int threads = ctx->spec.threads_per_tile;
-    raster_tiles_kernel<kChipQueueCapacity><<<nTiles, threads, 0, ctx->stream>>>(P, tileBase);
+    static int ctasPerSm = 0, numSms = 0;
+    if (!ctasPerSm) {
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, raster_warps_kernel, kWarpsPerCta * 32, 0));
+        GUDNI_CUDA_TRY(ctx, cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, ctx->device));
+        if (ctasPerSm < 1) ctasPerSm = 1;
+    }
+    unsigned int* workCounter = reinterpret_cast<unsigned int*>(ctx->counters.as<unsigned long long>() + 3);
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(workCounter, 0, sizeof(unsigned int), ctx->stream));
+    const long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
+    const int grid = (int)std::min<long long>((long long)ctasPerSm * numSms, (units + kWarpsPerCta - 1) / kWarpsPerCta);
+    raster_warps_kernel<<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles, workCounter);
     ctx->launches++;
     GUDNI_CUDA_TRY(ctx, cudaGetLastError());
     return GUDNI_OK;
