@@ -17,10 +17,16 @@ constexpr int kWarpsPerCta = 4;
 // work-group sliced by warps: `Work2D numTiles threadsPerTile` (OpenCL/CallKernels.hs:141-142).
 __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_warps_kernel(const FrameParams P, int tileBase, int nTiles,
                                                                          unsigned int* workCounter) {
-    __shared__ WarpScratch scratch[kWarpsPerCta];
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smemRaw);
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch& W = scratch[warp];
+    QueueCold<kQueueCap - kQueueHot> cold;
+    LaneQueue q;
+    q.cold = &cold;
+    q.thrHot = W.qThr + lane;
+    q.hdrHot = W.qHdr + lane;
     const int warpShift = P.computeDepth - 5;                    // warps per tile = threadsPerTile / 32
     const unsigned totalUnits = (unsigned)nTiles << warpShift;
     const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
@@ -35,13 +41,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_warps_kernel(const F
         int generated = -1;
         int failed = 0;
         if (tile.shape_count <= denseCap) {
-            failed = rasterWarpDense<ChipQueue<kChipQueueCapacity>>(P, W, tile, tileIndex, column, generated);
+            failed = rasterWarpDense(P, W, q, tile, tileIndex, column, generated);
         } else {
             // a tile that stopped splitting at the 8-pixel floor with more shapes than stack bits:
             // lane-private sweep with the bit -> shape table, colours through global memory
             const ThreadGeom g = threadGeom(P, tile, column);
             if (g.active) {
-                ChipQueue<kChipQueueCapacity> q;
                 const bool ok = rasterThread(P, *reinterpret_cast<const TileTable*>(&W), 0u, g, q,
                                              P.tileThreadBase[tileIndex] + column, generated);
                 failed = ok ? 0 : 1;
@@ -95,7 +100,10 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& P, int tileBase, int nTiles) 
     if (nTiles <= 0) return GUDNI_OK;
     static int ctasPerSm = 0, numSms = 0;
     if (!ctasPerSm) {
-        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, raster_warps_kernel, kWarpsPerCta * 32, 0));
+        GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_warps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(kWarpsPerCta * sizeof(WarpScratch))));
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, raster_warps_kernel, kWarpsPerCta * 32,
+                                                                          kWarpsPerCta * sizeof(WarpScratch)));
         GUDNI_CUDA_TRY(ctx, cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, ctx->device));
         if (ctasPerSm < 1) ctasPerSm = 1;
     }
@@ -103,7 +111,7 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& P, int tileBase, int nTiles) 
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(workCounter, 0, sizeof(unsigned int), ctx->stream));
     const long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
     const int grid = (int)std::min<long long>((long long)ctasPerSm * numSms, (units + kWarpsPerCta - 1) / kWarpsPerCta);
-    raster_warps_kernel<<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles, workCounter);
+    raster_warps_kernel<<<grid, kWarpsPerCta * 32, kWarpsPerCta * sizeof(WarpScratch), ctx->stream>>>(P, tileBase, nTiles, workCounter);
     ctx->launches++;
     GUDNI_CUDA_TRY(ctx, cudaGetLastError());
     return GUDNI_OK;

@@ -22,12 +22,14 @@
 
 namespace gudni_dev {
 
-constexpr int kSectionsPerRound = 4;
+constexpr int kSectionsPerRound = 2;
 constexpr int kWarpTableCap = 128;
+constexpr int kQueueCap = 64;      // thresholds per column-thread before the HBM replay takes over
+constexpr int kQueueHot = 10;      // of which in shared memory
 constexpr uint32_t kRecPixelEnd = 1u;
 
 struct SectionRec {   // 32 bytes
-    uint64_t hi, lo;  // shape stack the section is coloured with
+    uint64_t hi, lo;  // shape stack the section is coloured with; overwritten by its colour (float4)
     float area;
     uint32_t xy;      // absolute pixel x | y << 16 (picture substances only)
     uint32_t flags;
@@ -35,11 +37,13 @@ struct SectionRec {   // 32 bytes
 };
 
 struct WarpScratch {
-    float4 premul[kWarpTableCap];
-    uint32_t meta[kWarpTableCap];
-    SectionRec rec[32 * kSectionsPerRound];
-    float4 result[32 * kSectionsPerRound];
+    float4 premul[kWarpTableCap];                 //  2,048 B  tile substance table
+    uint32_t meta[kWarpTableCap];                 //    512 B
+    SectionRec rec[32 * kSectionsPerRound];       //  2,048 B  section records / their colours
+    float4 qThr[kQueueHot * 32];                  //  8,192 B  hot part of the 32 threshold queues
+    uint32_t qHdr[kQueueHot * 32];                //  2,048 B
 };
+typedef WarpQueue<kQueueCap, kQueueHot> LaneQueue;
 
 // determineColor (K.cl:1447-1513) for a dense tile: table index = stack bit.
 __device__ __forceinline__ float4 denseColor(const FrameParams& P, const WarpScratch& W, uint64_t hi, uint64_t lo,
@@ -66,9 +70,8 @@ __device__ __forceinline__ float4 denseColor(const FrameParams& P, const WarpScr
 // One warp, one (tile, 32-column group) of a dense tile.  Returns per lane: 0 = done or inactive,
 // 1 = the lane's threshold queue outgrew the on-chip capacity (caller hands it to the spill list).
 // `generated` receives the lane's qSlice.sLength after generation (-1 if inactive or spilled early).
-template <class Q>
-__device__ __forceinline__ int rasterWarpDense(const FrameParams& P, WarpScratch& W, const gudni_tile& tile, int tileIndex,
-                                               int column, int& generated) {
+__device__ __forceinline__ int rasterWarpDense(const FrameParams& P, WarpScratch& W, LaneQueue& q, const gudni_tile& tile,
+                                               int tileIndex, int column, int& generated) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const ThreadGeom g = threadGeom(P, tile, column);
@@ -81,7 +84,6 @@ __device__ __forceinline__ int rasterWarpDense(const FrameParams& P, WarpScratch
     }
     __syncwarp();
     // ---- generate + sort, lane-private -------------------------------------------------------------
-    Q q;
     ShapeStack stack{0ull, 0ull};
     SweepState st;
     const float floatHeight = (float)g.intHeight;
@@ -106,7 +108,6 @@ __device__ __forceinline__ int rasterWarpDense(const FrameParams& P, WarpScratch
     const float4 bgPremul = premultiply(P.background);
     uint32_t* outp = P.out + (size_t)(g.originY - P.rowOrigin) * P.width + g.originX;   // only dereferenced when active
     SectionRec* myRec = W.rec + lane * kSectionsPerRound;
-    const float4* myResult = W.result + lane * kSectionsPerRound;
     int wrow = 0;   // pixels of the slab stored so far (rows complete in order)
     while (__any_sync(full, st.alive)) {
         // ---- emit ---------------------------------------------------------------------------------
@@ -158,13 +159,13 @@ __device__ __forceinline__ int rasterWarpDense(const FrameParams& P, WarpScratch
             if (f < total) {
                 const int slot = owner * kSectionsPerRound + (f - ownerExcl);
                 const SectionRec r = W.rec[slot];
-                W.result[slot] = denseColor(P, W, r.hi, r.lo, bgPremul, r.xy);
+                *reinterpret_cast<float4*>(&W.rec[slot]) = denseColor(P, W, r.hi, r.lo, bgPremul, r.xy);
             }
         }
         __syncwarp();
         // ---- accumulate in section order (K.cl:1904) ----------------------------------------------
         for (int j = 0; j < count; j++) {
-            const float4 color = myResult[j];
+            const float4 color = *reinterpret_cast<const float4*>(&myRec[j]);
             const float area = myRec[j].area;
             st.accR += color.x * area;
             st.accG += color.y * area;
