@@ -87,7 +87,7 @@ int beginFrameCommon(gudni_ctx* ctx, const float bg[4], int width, int height, i
     ctx->firstKernelRecorded = false;
     ctx->binUsed = false;
     ctx->inFrame = true;
-    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, 64, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, 256, ctx->stream));
     return GUDNI_OK;
 }
 
@@ -137,7 +137,7 @@ int gudni_b200_init(int device, const gudni_spec* want, gudni_spec* got, gudni_c
                           &ctx->evDownloadDone, &ctx->evFirstKernel};
     for (cudaEvent_t* e : evs)
         if (cudaEventCreate(e) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
-    if (devEnsure(ctx, ctx->counters, 64) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
+    if (devEnsure(ctx, ctx->counters, 256) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
     ctx->spillCapacity = kSpillListCapacity;
     if (devEnsure(ctx, ctx->spillList, (size_t)kSpillListCapacity * 8) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
     ctx->spillSlots = kSpillSlots;
@@ -334,13 +334,17 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
         GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(out_bgra, src, rows * ctx->width * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evDownloadDone, ctx->stream));
-    unsigned long long counters[8] = {0};
-    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(counters, ctx->counters.ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long counters[32] = {0};
+    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(counters, ctx->counters.ptr, 256, cudaMemcpyDeviceToHost, ctx->stream));
     unsigned long long binCounters[8] = {0};
     if (ctx->binUsed)
         GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(binCounters, ctx->binCounters.ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->inFrame = false;
+#ifdef GUDNI_STATS
+    fprintf(stderr, "[stats] sections %llu hits %llu parks %llu rounds %llu evals %llu zero-area %llu\n", counters[8], counters[9],
+            counters[10], counters[11], counters[12], counters[13]);
+#endif
     if (binCounters[4])
         return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "a minimum-size tile lists more than 65535 shapes: unsupported by the raster kernels");
     gudni_stats s{};
