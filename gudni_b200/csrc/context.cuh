@@ -55,6 +55,8 @@ struct gudni_ctx {
     DevBuf spillList;       // u32 per spilled thread
     int spillCapacity = 0;
     DevBuf spillThr, spillHdr;
+    DevBuf thrStore, hdrStore, threadRecs;   // generate -> sweep hand-over
+    unsigned long long storeCap = 0;
     int spillSlots = 0;
 
     // taps

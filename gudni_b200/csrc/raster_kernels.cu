@@ -8,28 +8,39 @@
 
 using namespace gudni_dev;
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kGenWarpsPerCta = 4;
+constexpr int kSweepWarpsPerCta = 2;
 
-// Fused generate -> sort -> sweep, persistent: the grid is sized to what the chip holds resident and
-// every warp pulls (tile, 32-column group) units from a global counter until the frame is done, so
-// a warp that draws a cheap unit moves on instead of waiting at a CTA barrier for the slowest warp
-// of its tile, and the tail of the frame is spread over all SMs.  The unit is the reference's
-// work-group sliced by warps: `Work2D numTiles threadsPerTile` (OpenCL/CallKernels.hs:141-142).
-__global__ void __launch_bounds__(kWarpsPerCta * 32) raster_warps_kernel(const FrameParams P, int tileBase, int nTiles,
-                                                                         unsigned int* workCounter) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smemRaw);
+// The frame is rasterized by two persistent kernels.  Both size their grid to what the chip holds
+// resident and every warp pulls (tile, 32-column group) units from a global counter until the frame
+// is done; the unit is the reference's work-group sliced by warps (`Work2D numTiles threadsPerTile`,
+// OpenCL/CallKernels.hs:141-142).
+//   raster_generate_kernel   generateThresholds + sortThresholds (K.cl:2030-2115): queues built and
+//                            sorted in shared memory, packed into HBM once (20 B per threshold)
+//   raster_sweep_kernel      renderThresholds (K.cl:2117-2167): substance table, colour cache,
+//                            pending list and the hot part of the queues in shared memory
+// Splitting them halves the instruction footprint each warp drags through the instruction cache
+// (one fused kernel saturated it) and lets each phase have the occupancy it needs.
+__device__ __forceinline__ void registerSpill(const FrameParams& P, int tileIndex, int column) {
+    // replayed by raster_spill_kernel against an HBM queue of MAXTHRESHOLDS entries
+    const unsigned long long slot = atomicAdd(&P.counters[kCntSpilled], 1ull);
+    if (slot < (unsigned long long)P.spillCapacity)
+        P.spillList[slot] = ((unsigned long long)tileIndex << 32) | (unsigned long long)column;
+}
+
+__global__ void __launch_bounds__(kGenWarpsPerCta * 32) raster_generate_kernel(const FrameParams P, int tileBase, int nTiles) {
+    __shared__ GenScratch scratch[kGenWarpsPerCta];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpScratch& W = scratch[warp];
-    QueueCold<kQueueCap - kQueueHot> cold;
-    LaneQueue q;
+    QueueCold<kQueueCap - kGenQueueHot> cold;
+    GenQueue q;
     q.cold = &cold;
-    q.thrHot = W.qThr + lane;
-    q.hdrHot = W.qHdr + lane;
+    q.thrHot = scratch[warp].qThr + lane;
+    q.hdrHot = scratch[warp].qHdr + lane;
     const int warpShift = P.computeDepth - 5;                    // warps per tile = threadsPerTile / 32
     const unsigned totalUnits = (unsigned)nTiles << warpShift;
     const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
+    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkGenerate);
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd(workCounter, 1u);
@@ -41,27 +52,55 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_warps_kernel(const F
         int generated = -1;
         int failed = 0;
         if (tile.shape_count <= denseCap) {
-            failed = rasterWarpDense(P, W, q, tile, tileIndex, column, generated);
+            failed = generateWarp(P, q, tile, tileIndex, (unsigned)tileBase * (1u << warpShift) + unit, column, generated);
         } else {
             // a tile that stopped splitting at the 8-pixel floor with more shapes than stack bits:
-            // lane-private sweep with the bit -> shape table, colours through global memory
+            // its threads take the lane-private replay path (bit -> shape table, HBM queue)
             const ThreadGeom g = threadGeom(P, tile, column);
-            if (g.active) {
-                const bool ok = rasterThread(P, *reinterpret_cast<const TileTable*>(&W), 0u, g, q,
-                                             P.tileThreadBase[tileIndex] + column, generated);
-                failed = ok ? 0 : 1;
-            }
+            ThreadRec rec{};
+            rec.count = kRecInactive;
+            P.threadRecs[((size_t)tileBase * (1u << warpShift) + unit) * 32 + lane] = rec;
+            failed = g.active ? 1 : 0;
         }
-        __syncwarp();
-        // statistics: thresholds of lanes that completed here (spilled lanes are counted by the replay)
+        // statistics: thresholds of lanes that completed here (replayed lanes are counted by the replay)
         unsigned int mine = (!failed && generated > 0) ? (unsigned)generated : 0u;
         for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(full, mine, d);
         if (lane == 0 && mine) atomicAdd(&P.counters[kCntThresholds], (unsigned long long)mine);
+        if (failed) registerSpill(P, tileIndex, column);
+    }
+}
+
+__global__ void __launch_bounds__(kSweepWarpsPerCta * 32) raster_sweep_kernel(const FrameParams P, int tileBase, int nTiles) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smemRaw);
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpScratch& W = scratch[warp];
+    QueueCold<kQueueCap - kQueueHot> cold;
+    LaneLog log;
+    LaneQueue q;
+    q.cold = &cold;
+    q.thrHot = W.qThr + lane;
+    q.hdrHot = W.qHdr + lane;
+    const int warpShift = P.computeDepth - 5;
+    const unsigned totalUnits = (unsigned)nTiles << warpShift;
+    const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
+    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkSweep);
+    for (;;) {
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd(workCounter, 1u);
+        unit = __shfl_sync(full, unit, 0);
+        if (unit >= totalUnits) break;
+        const int tileIndex = tileBase + (int)(unit >> warpShift);
+        const int column = (int)((unit & ((1u << warpShift) - 1u)) << 5) + lane;
+        const gudni_tile tile = P.tiles[tileIndex];
+        if (tile.shape_count > denseCap) continue;   // replayed lane-privately
+        const int failed = sweepWarp(P, W, q, log, tile, (unsigned)tileBase * (1u << warpShift) + unit, column);
         if (failed) {
-            // replayed by raster_spill_kernel against an HBM queue of MAXTHRESHOLDS entries
-            const unsigned long long slot = atomicAdd(&P.counters[kCntSpilled], 1ull);
-            if (slot < (unsigned long long)P.spillCapacity)
-                P.spillList[slot] = ((unsigned long long)tileIndex << 32) | (unsigned long long)column;
+            // its thresholds were counted by the generate kernel; the replay counts them again
+            const ThreadRec rec = P.threadRecs[((size_t)tileBase * (1u << warpShift) + unit) * 32 + lane];
+            atomicAdd(&P.counters[kCntThresholds], 0ull - (unsigned long long)rec.count);
+            registerSpill(P, tileIndex, column);
         }
     }
 }
@@ -98,21 +137,27 @@ namespace gudni_launch {
 
 int rasterTiles(gudni_ctx* ctx, const FrameParams& P, int tileBase, int nTiles) {
     if (nTiles <= 0) return GUDNI_OK;
-    static int ctasPerSm = 0, numSms = 0;
-    if (!ctasPerSm) {
-        GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_warps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(kWarpsPerCta * sizeof(WarpScratch))));
-        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, raster_warps_kernel, kWarpsPerCta * 32,
-                                                                          kWarpsPerCta * sizeof(WarpScratch)));
+    static int genCtasPerSm = 0, sweepCtasPerSm = 0, numSms = 0;
+    const size_t sweepSmem = kSweepWarpsPerCta * sizeof(WarpScratch);
+    if (!genCtasPerSm) {
+        GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweepSmem));
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sweepCtasPerSm, raster_sweep_kernel,
+                                                                          kSweepWarpsPerCta * 32, sweepSmem));
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&genCtasPerSm, raster_generate_kernel,
+                                                                          kGenWarpsPerCta * 32, 0));
         GUDNI_CUDA_TRY(ctx, cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, ctx->device));
-        if (ctasPerSm < 1) ctasPerSm = 1;
+        if (genCtasPerSm < 1) genCtasPerSm = 1;
+        if (sweepCtasPerSm < 1) sweepCtasPerSm = 1;
     }
-    unsigned int* workCounter = reinterpret_cast<unsigned int*>(ctx->counters.as<unsigned long long>() + 3);
-    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(workCounter, 0, sizeof(unsigned int), ctx->stream));
+    // work counters of the two kernels (the threshold store cursor runs on across the jobs of a frame)
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkGenerate, 0, 8, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkSweep, 0, 8, ctx->stream));
     const long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
-    const int grid = (int)std::min<long long>((long long)ctasPerSm * numSms, (units + kWarpsPerCta - 1) / kWarpsPerCta);
-    raster_warps_kernel<<<grid, kWarpsPerCta * 32, kWarpsPerCta * sizeof(WarpScratch), ctx->stream>>>(P, tileBase, nTiles, workCounter);
-    ctx->launches++;
+    const int genGrid = (int)std::min<long long>((long long)genCtasPerSm * numSms, (units + kGenWarpsPerCta - 1) / kGenWarpsPerCta);
+    const int sweepGrid = (int)std::min<long long>((long long)sweepCtasPerSm * numSms, (units + kSweepWarpsPerCta - 1) / kSweepWarpsPerCta);
+    raster_generate_kernel<<<genGrid, kGenWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
+    raster_sweep_kernel<<<sweepGrid, kSweepWarpsPerCta * 32, sweepSmem, ctx->stream>>>(P, tileBase, nTiles);
+    ctx->launches += 2;
     GUDNI_CUDA_TRY(ctx, cudaGetLastError());
     return GUDNI_OK;
 }

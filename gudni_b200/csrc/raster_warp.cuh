@@ -2,22 +2,25 @@
 //
 // The reference gives each work-item the whole job of its column: generate, sort, sweep, and for
 // every section of the sweep a walk down the shape stack compositing every translucent layer
-// (Kernels.cl:1881-1916, 1447-1513).  On deep scenes that walk is > 80 % of the arithmetic, and it
-// is massively redundant: the colour of a section is a pure function of the set of shapes present
-// (for solid substances), and the sections of a pixel, of the pixel below and of the neighbouring
-// columns keep meeting the same few sets.
+// (Kernels.cl:1881-1916, 1447-1513).  On deep scenes that walk is > 80 % of the arithmetic, it is
+// redundant (the colour of a section is a pure function of the set of shapes present, and the
+// sections of a pixel, of the pixel below and of the neighbouring columns keep meeting the same
+// sets), and its length differs from lane to lane.
 //
 // For "dense" tiles (no more shapes than MAXSHAPE: every tile above the 8-pixel floor) a shape's
 // stack bit is its position in the tile's list, so the 128-bit stack is the same key in every lane
-// of every warp working on the tile.  Each warp keeps
-//   * the tile's substance table in shared memory (premultiplied colour + meta word per bit), and
-//   * a direct-mapped colour cache in shared memory keyed by the stack.
-// A lane sweeps lane-privately (cheap bookkeeping) and looks every non-empty section up in the
-// cache; on a miss it parks.  When every lane is parked or finished, the parked lanes elect one
-// owner per cache line (a 4-byte claim word), the owners composite their stack once
-// (determineColor, operation for operation as the reference), publish it, and everyone resumes.
-// Each lane still adds colour * area into its own accumulators in section order, so pixels are
-// bit-identical to the reference; only the number of times a colour is recomputed changes.
+// of the warp.  The warp keeps in shared memory
+//   * the tile's substance table (premultiplied colour + meta word per bit),
+//   * a direct-mapped cache of colours keyed by the stack, and
+//   * a list of stacks met but not composited yet ("pending").
+// Lanes sweep lane-privately in band-synchronous rounds (the branchy band bookkeeping is reached by
+// all lanes together).  A section whose stack hits the cache is accumulated at once; otherwise the
+// stack joins the pending list (deduplicated) and the lane appends {reference, area} to a private
+// log and keeps sweeping.  When about a warp's worth of stacks is pending they are composited, one
+// per lane with all lanes busy (determineColor, operation for operation as the reference), and
+// every lane replays its log.  Each lane still adds colour * area into its own accumulators in
+// section order (K.cl:1904), so pixels are bit-identical to the reference; what changes is how often
+// a colour is recomputed and how many lanes work while it is.
 #pragma once
 #include "raster_device.cuh"
 
@@ -25,25 +28,39 @@ namespace gudni_dev {
 
 constexpr int kWarpTableCap = 128;
 constexpr int kQueueCap = 64;          // thresholds per column-thread before the HBM replay takes over
-constexpr int kQueueHot = 16;          // of which in shared memory
-constexpr int kColorCacheLines = 64;   // direct mapped
-constexpr int kSectionsPerRound = 4;   // section records a lane may park per round
+constexpr int kQueueHot = 8;           // of which in shared memory (sweep kernel)
+constexpr int kGenQueueHot = 16;       // ... (generate kernel)
+constexpr int kColorCacheLines = 128;  // direct mapped
+constexpr int kSectionsPerRound = 4;   // section records a lane may hand to the resolver per round
+constexpr int kPendingCap = 64;        // stacks waiting to be composited
+constexpr int kPendingFlush = 27;      // composite when this many are waiting (one per lane, most lanes busy)
+constexpr int kLogCap = 40;            // per-lane log entries between flushes
+constexpr uint8_t kLogInline = 0xFF;   // entry carries its colour
+constexpr uint8_t kLogPixelEnd = 0xFE; // marker: store the pixel
 
 struct WarpScratch {
     float4 premul[kWarpTableCap];                    // 2,048 B  tile substance table
     uint32_t meta[kWarpTableCap];                    //   512 B
-    ulonglong2 cacheKey[kColorCacheLines];           // 1,024 B  colour cache: stack (lo, hi)
-    float4 cacheColor[kColorCacheLines];             // 1,024 B  colour; w < 0 marks an empty line
-    uint32_t cacheClaim[kColorCacheLines];           //   256 B  lane that owns the line this pass
-    ulonglong2 recKey[32 * kSectionsPerRound];       // 2,048 B  parked sections: stack, then (aliased) colour
+    ulonglong2 cacheKey[kColorCacheLines];           // 2,048 B  colour cache: stack (lo, hi)
+    float4 cacheColor[kColorCacheLines];             // 2,048 B  colour; w < 0 marks an empty line
+    uint32_t cacheClaim[kColorCacheLines];           //   512 B
+    ulonglong2 pendKey[kPendingCap];                 // 1,024 B  stacks to composite
+    float4 pendColor[kPendingCap];                   // 1,024 B  ... and their colours once composited
+    ulonglong2 recKey[32 * kSectionsPerRound];       // 2,048 B  records of the round: stack, then colour / reference
     float recArea[32 * kSectionsPerRound];           //   512 B
-    float4 qThr[kQueueHot * 32];                     // 8,192 B  hot part of the 32 threshold queues
-    uint32_t qHdr[kQueueHot * 32];                   // 2,048 B
+    float4 qThr[kQueueHot * 32];                     // 4,096 B  hot part of the 32 threshold queues
+    uint32_t qHdr[kQueueHot * 32];                   // 1,024 B
 };
 typedef WarpQueue<kQueueCap, kQueueHot> LaneQueue;
 
+// per-lane log of sections whose colour was not known when they were swept
+struct LaneLog {
+    float4 rec[kLogCap];    // inline: (r, g, b, area); pending reference: (-, -, -, area)
+    uint8_t tag[kLogCap];   // kLogInline | kLogPixelEnd | pending index
+};
+
 // determineColor (K.cl:1447-1513) for a dense tile: table index = stack bit.
-__device__ __forceinline__ float4 denseColor(const FrameParams& P, const WarpScratch& W, uint64_t hi, uint64_t lo,
+static __device__ __noinline__ float4 denseColor(const FrameParams& P, const WarpScratch& W, uint64_t hi, uint64_t lo,
                                              float4 bgPremul, int absX, int absY) {
     float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t lastId = 0xFFFFFFFFu;
@@ -72,11 +89,73 @@ __device__ __forceinline__ uint32_t stackHash(uint64_t hi, uint64_t lo) {
     return (t >> 20) & (uint32_t)(kColorCacheLines - 1);
 }
 
-// One warp, one (tile, 32-column group) of a dense tile.  Returns per lane: 0 = done or inactive,
-// 1 = the lane's threshold queue outgrew the on-chip capacity (caller hands it to the spill list).
-// `generated` receives the lane's qSlice.sLength after generation (-1 if inactive or spilled early).
-__device__ __forceinline__ int rasterWarpDense(const FrameParams& P, WarpScratch& W, LaneQueue& q, const gudni_tile& tile,
-                                               int tileIndex, int column, int& generated) {
+// ---- generate kernel body -----------------------------------------------------------------------
+// One warp, one (tile, 32-column group) of a dense tile: every lane builds and sorts the threshold
+// queue of its column-thread (K.cl:2030-2115) in the warp's shared memory, then the warp packs the
+// queues into the frame-wide store with one atomic (a warp prefix sum gives each lane its offset).
+// Returns per lane 1 if the thread must be replayed against the HBM queue.
+struct GenScratch {
+    float4 qThr[kGenQueueHot * 32];
+    uint32_t qHdr[kGenQueueHot * 32];
+};
+typedef WarpQueue<kQueueCap, kGenQueueHot> GenQueue;
+
+__device__ __forceinline__ int generateWarp(const FrameParams& P, GenQueue& q, const gudni_tile& tile, int tileIndex,
+                                            unsigned unit, int column, int& generated) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const ThreadGeom g = threadGeom(P, tile, column);
+    ShapeStack stack{0ull, 0ull};
+    bool spilled = false;
+    generated = -1;
+    int count = 0;
+    if (g.active) {
+        q.init();
+        const uint32_t bits = buildThresholds<true>(P, g, q, stack, nullptr);
+        if (q.failed()) {
+            spilled = true;
+        } else {
+            generated = q.len;
+            const int threadId = P.tileThreadBase[tileIndex] + column;
+            if (P.dbgThresholds) P.dbgThresholds[threadId] = q.len;
+            if (P.dbgShapeBits) P.dbgShapeBits[threadId] = (int32_t)bits;
+            sortQueue(q);
+            count = q.len;
+        }
+    }
+    int incl = count;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(full, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(full, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && total) base = atomicAdd(&P.counters[kCntStoreCursor], (unsigned long long)total);
+    base = __shfl_sync(full, base, 0);
+    if (base + (unsigned long long)total > P.storeCap) {   // store exhausted: the replay kernel takes the warp's threads
+        spilled = spilled || g.active;
+        count = 0;
+    }
+    const unsigned int offset = (unsigned int)(base + (unsigned long long)(incl - count));
+    for (int i = 0; i < count; i++) {
+        const Thr t = q.getT(i);
+        P.thrStore[offset + i] = make_float4(t.top, t.bottom, t.left, t.right);
+        P.hdrStore[offset + i] = q.getH(i);
+    }
+    ThreadRec rec;
+    rec.hi = stack.hi; rec.lo = stack.lo;
+    rec.offset = offset;
+    rec.count = (g.active && !spilled) ? (unsigned int)count : kRecInactive;
+    rec.pad0 = rec.pad1 = 0u;
+    P.threadRecs[(size_t)unit * 32 + lane] = rec;
+    return spilled ? 1 : 0;
+}
+
+// ---- sweep kernel body --------------------------------------------------------------------------------
+// One warp, one (tile, 32-column group) of a dense tile.  Returns per lane 1 if the lane's threshold
+// queue outgrew the on-chip capacity while slicing (caller hands it to the spill list).
+__device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, LaneQueue& q, LaneLog& log,
+                                         const gudni_tile& tile, unsigned unit, int column) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const ThreadGeom g = threadGeom(P, tile, column);
@@ -92,44 +171,94 @@ __device__ __forceinline__ int rasterWarpDense(const FrameParams& P, WarpScratch
     // a picture's colour depends on the pixel, so stacks are only a valid key without pictures
     const bool cacheable = !__any_sync(full, anyPicture);
     for (int i = lane; i < kColorCacheLines; i += 32) W.cacheColor[i] = make_float4(0.f, 0.f, 0.f, -1.f);
-    __syncwarp();
-    // ---- generate + sort, lane-private -------------------------------------------------------------
-    ShapeStack stack{0ull, 0ull};
+    // ---- the thread's sorted queue and initial stack, from the generate kernel ------------------------
+    const ThreadRec rec = P.threadRecs[(size_t)unit * 32 + lane];
+    ShapeStack stack;
+    stack.hi = rec.hi;
+    stack.lo = rec.lo;
     SweepState st;
     const float floatHeight = (float)g.intHeight;
     bool spilled = false;
-    generated = -1;
     st.alive = false;
-    if (g.active) {
-        q.init();
-        const uint32_t bits = buildThresholds<true>(P, g, q, stack, nullptr);
-        if (q.failed()) {
-            spilled = true;
-        } else {
-            generated = q.len;
-            const int threadId = P.tileThreadBase[tileIndex] + column;
-            if (P.dbgThresholds) P.dbgThresholds[threadId] = q.len;
-            if (P.dbgShapeBits) P.dbgShapeBits[threadId] = (int32_t)bits;
-            sortQueue(q);
-            st.init(floatHeight);
+    q.init();
+    if (rec.count != kRecInactive) {
+        q.start = kQueueCap - (int)rec.count;
+        q.len = (int)rec.count;
+        for (int i = 0; i < (int)rec.count; i++) {
+            const float4 t = P.thrStore[rec.offset + i];
+            q.set(i, P.hdrStore[rec.offset + i], Thr{t.x, t.y, t.z, t.w});
         }
+        st.init(floatHeight);
     }
-    // ---- sweep, band-synchronous rounds ---------------------------------------------------------------
-    // Every round a lane (A) closes the pixel and opens the next band if it stands at a band boundary
-    // — the expensive, branchy part, which the lanes therefore reach together — then (B) walks up to
-    // kSectionsPerRound sections of the band, parking {stack, area} records; (C) the warp resolves
-    // the colours of all parked records through the colour cache, compositing each missing stack
-    // once; (D) each lane adds colour * area of its records in section order (K.cl:1904).
+    __syncwarp();
+    // ---- sweep -----------------------------------------------------------------------------------------
     const float4 bgPremul = premultiply(P.background);
     uint32_t* outp = P.out + (size_t)(g.originY - P.rowOrigin) * P.width + g.originX;   // only dereferenced when active
     ulonglong2* myKey = W.recKey + lane * kSectionsPerRound;
     float* myArea = W.recArea + lane * kSectionsPerRound;
-    while (__any_sync(full, st.alive)) {
-        // ---- (A) band boundary --------------------------------------------------------------------
+    int logLen = 0;        // entries in this lane's log
+    int wrow = 0;          // pixels of the slab stored so far (rows complete in order)
+    int pendingCount = 0;  // warp-uniform
+    for (;;) {
+        const bool anyAlive = __any_sync(full, st.alive);
+        // ---- flush: composite the pending stacks, replay the logs ----------------------------------
+        const bool logFull = logLen > kLogCap - (kSectionsPerRound + 2);
+        if (pendingCount >= kPendingFlush || !anyAlive || __any_sync(full, logFull)) {
+            for (int p0 = 0; p0 < pendingCount; p0 += 32) {
+                const int p = p0 + lane;
+                if (p < pendingCount) {
+                    const ulonglong2 key = W.pendKey[p];
+                    const float4 c = denseColor(P, W, key.y, key.x, bgPremul, 0, 0);
+                    W.pendColor[p] = c;
+                    W.cacheClaim[stackHash(key.y, key.x)] = (uint32_t)p;
+                }
+            }
+            __syncwarp();
+            for (int p0 = 0; p0 < pendingCount; p0 += 32) {   // publish to the cache, one winner per line
+                const int p = p0 + lane;
+                if (p < pendingCount) {
+                    const ulonglong2 key = W.pendKey[p];
+                    const uint32_t line = stackHash(key.y, key.x);
+                    if (W.cacheClaim[line] == (uint32_t)p) {
+                        const float4 c = W.pendColor[p];
+                        W.cacheKey[line] = key;
+                        W.cacheColor[line] = make_float4(c.x, c.y, c.z, 1.f);
+                    }
+                }
+            }
+            for (int j = 0; j < logLen; j++) {   // replay in section order (K.cl:1904)
+                const uint8_t tag = log.tag[j];
+                if (tag == kLogPixelEnd) {
+                    outp[(size_t)wrow * P.width] = pixelWord(st.accR, st.accG, st.accB, st.accArea);
+                    st.accR = st.accG = st.accB = st.accArea = 0.f;
+                    wrow++;
+                    continue;
+                }
+                float4 r = log.rec[j];
+                if (tag != kLogInline) {
+                    const float4 c = W.pendColor[tag];
+                    r.x = c.x; r.y = c.y; r.z = c.z;
+                }
+                st.accR += r.x * r.w;
+                st.accG += r.y * r.w;
+                st.accB += r.z * r.w;
+                st.accArea += r.w;
+            }
+            logLen = 0;
+            pendingCount = 0;
+            __syncwarp();
+            if (!anyAlive) break;
+        }
+        // ---- (A) band boundary: close the pixel, open the next band ---------------------------------
         if (st.alive && st.ex == 1.0f) {
             if (st.ey >= st.pixelY) {   // calculatePixel's loop condition failed: the pixel is complete
-                outp[(size_t)st.row * P.width] = pixelWord(st.accR, st.accG, st.accB, st.accArea);
-                st.accR = st.accG = st.accB = st.accArea = 0.f;
+                if (logLen == 0) {      // everything of this pixel is accumulated
+                    outp[(size_t)wrow * P.width] = pixelWord(st.accR, st.accG, st.accB, st.accArea);
+                    st.accR = st.accG = st.accB = st.accArea = 0.f;
+                    wrow++;
+                } else {
+                    log.tag[logLen++] = kLogPixelEnd;
+                }
                 nextPixel(st, floatHeight);
             }
             if (st.alive) {
@@ -137,7 +266,7 @@ __device__ __forceinline__ int rasterWarpDense(const FrameParams& P, WarpScratch
                 if (q.failed()) { spilled = true; st.alive = false; }
             }
         }
-        // ---- (B) sections of the band ---------------------------------------------------------------
+        // ---- (B) up to kSectionsPerRound sections of the band ---------------------------------------
         int count = 0;
         while (st.alive && count < kSectionsPerRound) {
             float area;
@@ -150,14 +279,14 @@ __device__ __forceinline__ int rasterWarpDense(const FrameParams& P, WarpScratch
             }
             if (st.ex == 1.0f) break;   // band finished: next round starts at (A)
         }
-        // ---- (C) resolve colours --------------------------------------------------------------------
+        // ---- (C) resolve the records: cache hit -> colour, else -> reference to a pending stack -------
         if (!cacheable) {
-            // picture substances: the colour depends on the pixel, every lane composites its own records
+            // picture substances: the colour depends on the pixel; every lane composites its own records
             // (all of them lie in the pixel row the lane is sweeping)
             for (int j = 0; j < count; j++) {
                 const ulonglong2 key = myKey[j];
-                const float4 color = denseColor(P, W, key.y, key.x, bgPremul, g.originX, g.originY + st.row);
-                *reinterpret_cast<float4*>(&myKey[j]) = color;
+                const float4 c = denseColor(P, W, key.y, key.x, bgPremul, g.originX, g.originY + st.row);
+                *reinterpret_cast<float4*>(&myKey[j]) = make_float4(c.x, c.y, c.z, 1.f);
             }
         } else {
             int incl = count;
@@ -181,46 +310,64 @@ __device__ __forceinline__ int rasterWarpDense(const FrameParams& P, WarpScratch
                 const bool valid = f < total;
                 const int slot = valid ? lo_ * kSectionsPerRound + (f - ownerExcl) : 0;
                 ulonglong2 key = make_ulonglong2(0ull, 0ull);
-                uint32_t line = 0;
-                bool need = false;
-                float4 color = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool miss = false;
+                float4 out = make_float4(0.f, 0.f, 0.f, 0.f);   // w = 1: colour; w = -(1 + pending index): reference
                 if (valid) {
                     key = W.recKey[slot];
-                    line = stackHash(key.y, key.x);
+                    const uint32_t line = stackHash(key.y, key.x);
                     const float4 c = W.cacheColor[line];
                     const ulonglong2 k = W.cacheKey[line];
-                    if (c.w >= 0.f && k.x == key.x && k.y == key.y) color = c;
-                    else need = true;
+                    if (c.w >= 0.f && k.x == key.x && k.y == key.y) out = c;
+                    else miss = true;
                 }
-                if (__any_sync(full, need)) {
-                    // one owner per cache line composites; lanes holding the same stack share the result
-                    if (need) W.cacheClaim[line] = (uint32_t)lane;
-                    __syncwarp();
-                    const bool owner = need && W.cacheClaim[line] == (uint32_t)lane;
-                    if (owner) {
-                        color = denseColor(P, W, key.y, key.x, bgPremul, 0, 0);
-                        W.cacheKey[line] = key;
-                        W.cacheColor[line] = make_float4(color.x, color.y, color.z, 1.f);
+                // misses, one after the other: already pending? else append (or composite on the spot
+                // if the list is full — more than kPendingCap new stacks in flight is rare)
+                unsigned todo = __ballot_sync(full, miss);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const unsigned long long kx = __shfl_sync(full, key.x, src), ky = __shfl_sync(full, key.y, src);
+                    bool match = false;
+                    int matchIdx = 0;
+                    for (int p = lane; p < pendingCount; p += 32) {
+                        const ulonglong2 k = W.pendKey[p];
+                        if (k.x == kx && k.y == ky) { match = true; matchIdx = p; }
                     }
-                    __syncwarp();
-                    if (need && !owner) {
-                        const ulonglong2 k = W.cacheKey[line];
-                        if (k.x == key.x && k.y == key.y) color = W.cacheColor[line];
-                        else color = denseColor(P, W, key.y, key.x, bgPremul, 0, 0);   // lost the line to another stack
+                    const unsigned found = __ballot_sync(full, match);
+                    int idx;
+                    if (found) {
+                        idx = __shfl_sync(full, matchIdx, __ffs(found) - 1);
+                    } else if (pendingCount < kPendingCap) {
+                        idx = pendingCount;
+                        if (lane == 0) W.pendKey[idx] = make_ulonglong2(kx, ky);
+                        pendingCount++;
+                        __syncwarp();
+                    } else {
+                        idx = -1;
+                    }
+                    if (lane == src) {
+                        if (idx >= 0) out.w = -(float)(1 + idx);
+                        else { const float4 c = denseColor(P, W, ky, kx, bgPremul, 0, 0); out = make_float4(c.x, c.y, c.z, 1.f); }
                     }
                 }
-                if (valid) *reinterpret_cast<float4*>(&W.recKey[slot]) = color;
+                if (valid) *reinterpret_cast<float4*>(&W.recKey[slot]) = out;
             }
+            __syncwarp();
         }
-        __syncwarp();
-        // ---- (D) accumulate in section order ----------------------------------------------------------
+        // ---- (D) accumulate what is known, log the rest, in section order ----------------------------
         for (int j = 0; j < count; j++) {
-            const float4 color = *reinterpret_cast<const float4*>(&myKey[j]);
+            const float4 r = *reinterpret_cast<const float4*>(&myKey[j]);
             const float area = myArea[j];
-            st.accR += color.x * area;
-            st.accG += color.y * area;
-            st.accB += color.z * area;
-            st.accArea += area;
+            if (r.w > 0.f && logLen == 0) {
+                st.accR += r.x * area;
+                st.accG += r.y * area;
+                st.accB += r.z * area;
+                st.accArea += area;
+            } else {
+                log.rec[logLen] = make_float4(r.x, r.y, r.z, area);
+                log.tag[logLen] = (r.w > 0.f) ? kLogInline : (uint8_t)(int)(-r.w - 1.f);
+                logLen++;
+            }
         }
         __syncwarp();
     }

@@ -48,6 +48,10 @@ FrameParams makeParams(gudni_ctx* ctx) {
     P.counters = ctx->counters.as<unsigned long long>();
     P.spillList = ctx->spillList.as<unsigned long long>();
     P.spillCapacity = ctx->spillCapacity;
+    P.thrStore = ctx->thrStore.as<float4>();
+    P.hdrStore = ctx->hdrStore.as<uint32_t>();
+    P.storeCap = ctx->storeCap;
+    P.threadRecs = ctx->threadRecs.as<gudni_dev::ThreadRec>();
     return P;
 }
 
@@ -55,6 +59,18 @@ int ensureFrameBuffer(gudni_ctx* ctx) {
     if (ctx->externalTarget) return GUDNI_OK;
     size_t bytes = (size_t)ctx->width * (size_t)(ctx->rowEnd - ctx->rowBegin) * 4;
     return devEnsure(ctx, ctx->frame, std::max<size_t>(bytes, 4));
+}
+
+// Hand-over buffers between the generate and the sweep kernel: 16 thresholds per column-thread on
+// average (threads that do not fit are replayed), one 32-byte record per thread.
+int ensureHandover(gudni_ctx* ctx, int64_t totalTiles) {
+    const size_t threads = (size_t)totalTiles * (size_t)ctx->spec.threads_per_tile;
+    const size_t entries = std::max<size_t>(threads * 16, (size_t)1 << 20);
+    GUDNI_TRY(devEnsure(ctx, ctx->thrStore, entries * 16));
+    GUDNI_TRY(devEnsure(ctx, ctx->hdrStore, entries * 4));
+    ctx->storeCap = std::min(ctx->thrStore.cap / 16, ctx->hdrStore.cap / 4);
+    GUDNI_TRY(devEnsure(ctx, ctx->threadRecs, std::max<size_t>(threads, 32) * sizeof(gudni_dev::ThreadRec)));
+    return GUDNI_OK;
 }
 
 int ensureDebug(gudni_ctx* ctx, int64_t columnsBefore, int64_t columnsAfter) {
@@ -153,7 +169,8 @@ void gudni_b200_destroy(gudni_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->geometry, &ctx->substances, &ctx->pictures, &ctx->pictureUses, &ctx->shapes, &ctx->tiles,
                       &ctx->tileThreadBase, &ctx->frame, &ctx->counters, &ctx->spillList, &ctx->spillThr, &ctx->spillHdr,
-                      &ctx->dbgThresholds, &ctx->dbgShapeBits, &ctx->entries, &ctx->binCounters};
+                      &ctx->dbgThresholds, &ctx->dbgShapeBits, &ctx->entries, &ctx->binCounters, &ctx->thrStore, &ctx->hdrStore,
+                      &ctx->threadRecs};
     for (DevBuf* b : bufs)
         if (b->ptr) cudaFree(b->ptr);
     for (DevBuf& b : ctx->binWork)
@@ -276,6 +293,7 @@ int gudni_b200_raster_job(gudni_ctx* ctx, const gudni_shape* shapes, int n_shape
     ctx->nShapes += n_shapes;
     ctx->nTiles += n_tiles;
     ctx->nColumns += columns_allocated;
+    GUDNI_TRY(ensureHandover(ctx, ctx->nTiles));
     markFirstKernel(ctx);
     GUDNI_TRY(gudni_launch::rasterTiles(ctx, makeParams(ctx), tileBase, n_tiles));
     ctx->rasteredTiles = ctx->nTiles;
@@ -288,6 +306,7 @@ static int rasterSceneCommon(gudni_ctx* ctx, const void* devEntries, int n_entri
     GUDNI_TRY(gudni_bin::binScene(ctx, static_cast<const gudni_shape_entry*>(devEntries), n_entries));
     GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evBinDone, ctx->stream));
     GUDNI_TRY(ensureDebug(ctx, 0, ctx->nColumns));
+    GUDNI_TRY(ensureHandover(ctx, ctx->nTiles));
     GUDNI_TRY(gudni_launch::rasterTiles(ctx, makeParams(ctx), 0, (int)ctx->nTiles));
     ctx->rasteredTiles = ctx->nTiles;
     return GUDNI_OK;
