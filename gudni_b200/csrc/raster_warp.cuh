@@ -170,7 +170,7 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
     }
     // a picture's colour depends on the pixel, so stacks are only a valid key without pictures
     const bool cacheable = !__any_sync(full, anyPicture);
-    for (int i = lane; i < kColorCacheLines; i += 32) W.cacheColor[i] = make_float4(0.f, 0.f, 0.f, -1.f);
+    for (int i = lane; i < kColorCacheLines; i += 32) W.cacheColor[i] = make_float4(0.f, 0.f, 0.f, -1000.f);
     // ---- the thread's sorted queue and initial stack, from the generate kernel ------------------------
     const ThreadRec rec = P.threadRecs[(size_t)unit * 32 + lane];
     ShapeStack stack;
@@ -210,22 +210,12 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                     const ulonglong2 key = W.pendKey[p];
                     const float4 c = denseColor(P, W, key.y, key.x, bgPremul, 0, 0);
                     W.pendColor[p] = c;
-                    W.cacheClaim[stackHash(key.y, key.x)] = (uint32_t)p;
+                    // un-pin: the line that references this entry (if it got one) now holds the colour
+                    const uint32_t line = stackHash(key.y, key.x);
+                    if (W.cacheColor[line].w == -(float)(1 + p)) W.cacheColor[line] = make_float4(c.x, c.y, c.z, 1.f);
                 }
             }
             __syncwarp();
-            for (int p0 = 0; p0 < pendingCount; p0 += 32) {   // publish to the cache, one winner per line
-                const int p = p0 + lane;
-                if (p < pendingCount) {
-                    const ulonglong2 key = W.pendKey[p];
-                    const uint32_t line = stackHash(key.y, key.x);
-                    if (W.cacheClaim[line] == (uint32_t)p) {
-                        const float4 c = W.pendColor[p];
-                        W.cacheKey[line] = key;
-                        W.cacheColor[line] = make_float4(c.x, c.y, c.z, 1.f);
-                    }
-                }
-            }
             for (int j = 0; j < logLen; j++) {   // replay in section order (K.cl:1904)
                 const uint8_t tag = log.tag[j];
                 if (tag == kLogPixelEnd) {
@@ -309,20 +299,51 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                 const int ownerExcl = __shfl_sync(full, excl, lo_);
                 const bool valid = f < total;
                 const int slot = valid ? lo_ * kSectionsPerRound + (f - ownerExcl) : 0;
+                // Cache line states (cacheColor.w): < 0 empty (-1000) or pending (-(1 + pending index),
+                // pinned until the flush); 1 ready.
                 ulonglong2 key = make_ulonglong2(0ull, 0ull);
-                bool miss = false;
+                uint32_t line = 0;
+                bool miss = false, slow = false;
                 float4 out = make_float4(0.f, 0.f, 0.f, 0.f);   // w = 1: colour; w = -(1 + pending index): reference
                 if (valid) {
                     key = W.recKey[slot];
-                    const uint32_t line = stackHash(key.y, key.x);
+                    line = stackHash(key.y, key.x);
                     const float4 c = W.cacheColor[line];
                     const ulonglong2 k = W.cacheKey[line];
-                    if (c.w >= 0.f && k.x == key.x && k.y == key.y) out = c;
+                    const bool same = k.x == key.x && k.y == key.y;
+                    if (same && c.w > -999.f) out = c;                       // ready colour or pending reference
+                    else if (c.w < 0.f && c.w > -999.f) slow = true;         // line pinned by another pending stack
                     else miss = true;
                 }
-                // misses, one after the other: already pending? else append (or composite on the spot
-                // if the list is full — more than kPendingCap new stacks in flight is rare)
-                unsigned todo = __ballot_sync(full, miss);
+                if (__any_sync(full, miss)) {
+                    // new stacks: one claimant per line appends it to the pending list and pins the line
+                    if (miss) W.cacheClaim[line] = (uint32_t)lane;
+                    __syncwarp();
+                    const bool winner = miss && W.cacheClaim[line] == (uint32_t)lane;
+                    const unsigned winners = __ballot_sync(full, winner);
+                    const int idx = pendingCount + __popc(winners & ((1u << lane) - 1u));
+                    if (winner) {
+                        if (idx < kPendingCap) {
+                            W.pendKey[idx] = key;
+                            W.cacheKey[line] = key;
+                            W.cacheColor[line] = make_float4(0.f, 0.f, 0.f, -(float)(1 + idx));
+                            out.w = -(float)(1 + idx);
+                        } else {   // more than kPendingCap new stacks in flight: composite on the spot (rare)
+                            const float4 c = denseColor(P, W, key.y, key.x, bgPremul, 0, 0);
+                            out = make_float4(c.x, c.y, c.z, 1.f);
+                        }
+                    }
+                    pendingCount = min(pendingCount + __popc(winners), kPendingCap);
+                    __syncwarp();
+                    if (miss && !winner) {   // lost the line: to the same stack (share it) or to another one
+                        const ulonglong2 k = W.cacheKey[line];
+                        const float4 c = W.cacheColor[line];
+                        if (k.x == key.x && k.y == key.y && c.w > -999.f) out = c;
+                        else slow = true;
+                    }
+                }
+                // leftovers, one after the other: already pending? else append without a cache line
+                unsigned todo = __ballot_sync(full, slow);
                 while (todo) {
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
