@@ -8,8 +8,14 @@
 
 using namespace gudni_dev;
 
-constexpr int kGenWarpsPerCta = 4;
-constexpr int kSweepWarpsPerCta = 2;
+#ifndef GUDNI_GEN_WARPS
+#define GUDNI_GEN_WARPS 4
+#endif
+#ifndef GUDNI_SWEEP_WARPS
+#define GUDNI_SWEEP_WARPS 2
+#endif
+constexpr int kGenWarpsPerCta = GUDNI_GEN_WARPS;
+constexpr int kSweepWarpsPerCta = GUDNI_SWEEP_WARPS;
 
 // The frame is rasterized by two persistent kernels.  Both size their grid to what the chip holds
 // resident and every warp pulls (tile, 32-column group) units from a global counter until the frame
@@ -133,7 +139,44 @@ __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, 
     }
 }
 
+// div3 against the compiler's IEEE division on pseudo-random operands (and the edge cases around
+// the fast-path window); counts bit mismatches.
+__global__ void selftest_div3_kernel(unsigned long long n, unsigned long long seed, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long z = seed + i * 0x9E3779B97F4A7C15ull;
+        float v[4];
+        for (int k = 0; k < 4; k++) {
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            const unsigned mode = (unsigned)(z >> 60);
+            float f = (float)((z >> 20) & 0xFFFFFFull) * (1.0f / 16777216.0f);   // [0,1)
+            if (mode == 0) f = __uint_as_float((unsigned)(z >> 8) & 0x7FFFFFFFu);    // any non-negative bit pattern
+            else if (mode == 1) f = f * 0x1p-58f;                                    // around the window's lower edge
+            else if (mode == 2) f = 0.0f;
+            else if (mode == 3) f = 1.0f;
+            v[k] = f;
+        }
+        const float d = v[3];
+        if (!(d > 0.0f) || isnan(v[0]) || isnan(v[1]) || isnan(v[2]) || isnan(d)) continue;
+        float qx, qy, qz;
+        div3(v[0], v[1], v[2], d, qx, qy, qz);
+        const float rx = v[0] / d, ry = v[1] / d, rz = v[2] / d;
+        bad += (__float_as_uint(qx) != __float_as_uint(rx)) + (__float_as_uint(qy) != __float_as_uint(ry)) +
+               (__float_as_uint(qz) != __float_as_uint(rz));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 namespace gudni_launch {
+int selftestDiv3(gudni_ctx* ctx, unsigned long long n, unsigned long long seed, unsigned long long* devMismatches) {
+    selftest_div3_kernel<<<148 * 8, 256, 0, ctx->stream>>>(n, seed, devMismatches);
+    ctx->launches++;
+    GUDNI_CUDA_TRY(ctx, cudaGetLastError());
+    return GUDNI_OK;
+}
 
 int rasterTiles(gudni_ctx* ctx, const FrameParams& P, int tileBase, int nTiles) {
     if (nTiles <= 0) return GUDNI_OK;

@@ -28,12 +28,27 @@ namespace gudni_dev {
 
 constexpr int kWarpTableCap = 128;
 constexpr int kQueueCap = 64;          // thresholds per column-thread before the HBM replay takes over
-constexpr int kQueueHot = 8;           // of which in shared memory (sweep kernel)
-constexpr int kGenQueueHot = 16;       // ... (generate kernel)
-constexpr int kColorCacheLines = 128;  // direct mapped
-constexpr int kSectionsPerRound = 4;   // section records a lane may hand to the resolver per round
-constexpr int kPendingCap = 64;        // stacks waiting to be composited
-constexpr int kPendingFlush = 27;      // composite when this many are waiting (one per lane, most lanes busy)
+#ifndef GUDNI_QUEUE_HOT
+#define GUDNI_QUEUE_HOT 12
+#endif
+constexpr int kQueueHot = GUDNI_QUEUE_HOT;           // of which in shared memory (sweep kernel)
+#ifndef GUDNI_GEN_QUEUE_HOT
+#define GUDNI_GEN_QUEUE_HOT 16
+#endif
+constexpr int kGenQueueHot = GUDNI_GEN_QUEUE_HOT;       // ... (generate kernel)
+#ifndef GUDNI_CACHE_LINES
+#define GUDNI_CACHE_LINES 128
+#endif
+constexpr int kColorCacheLines = GUDNI_CACHE_LINES;  // direct mapped
+#ifndef GUDNI_SECTIONS_PER_ROUND
+#define GUDNI_SECTIONS_PER_ROUND 6
+#endif
+constexpr int kSectionsPerRound = GUDNI_SECTIONS_PER_ROUND;   // section records a lane may hand to the resolver per round
+constexpr int kPendingCap = 48;        // stacks waiting to be composited
+#ifndef GUDNI_PENDING_FLUSH
+#define GUDNI_PENDING_FLUSH 27
+#endif
+constexpr int kPendingFlush = GUDNI_PENDING_FLUSH;      // composite when this many are waiting (one per lane, most lanes busy)
 constexpr int kLogCap = 40;            // per-lane log entries between flushes
 constexpr uint8_t kLogInline = 0xFF;   // entry carries its colour
 constexpr uint8_t kLogPixelEnd = 0xFE; // marker: store the pixel

@@ -486,6 +486,20 @@ int gudni_b200_launch_count(gudni_ctx* ctx, int64_t* n) {
     return GUDNI_OK;
 }
 
+int gudni_b200_debug_selftest(gudni_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+    if (!ctx || !mismatches) return GUDNI_ERR_ARGUMENT;
+    if (ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "selftest inside a frame");
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    unsigned long long* dev = ctx->counters.as<unsigned long long>() + 16;
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(dev, 0, 8, ctx->stream));
+    GUDNI_TRY(gudni_launch::selftestDiv3(ctx, n, seed, dev));
+    unsigned long long host = 0;
+    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(&host, dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *mismatches = host;
+    return GUDNI_OK;
+}
+
 int gudni_b200_debug_enable(gudni_ctx* ctx, int on) {
     if (!ctx) return GUDNI_ERR_ARGUMENT;
     ctx->debug = on != 0;

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "gudni_b200_ipc_export_frame", "gudni_b200_ipc_open", "gudni_b200_ipc_close", "gudni_b200_device_alloc",
     "gudni_b200_device_free", "gudni_b200_upload", "gudni_b200_download", "gudni_b200_frame_begin_device",
     "gudni_b200_raster_scene_device", "gudni_b200_sync", "gudni_b200_last_frame_ms", "gudni_b200_launch_count",
-    "gudni_b200_set_stream", "gudni_b200_debug_enable", "gudni_b200_debug_thread_counts", "gudni_b200_debug_binned",
+    "gudni_b200_set_stream", "gudni_b200_debug_selftest", "gudni_b200_debug_enable", "gudni_b200_debug_thread_counts", "gudni_b200_debug_binned",
     "gudni_b200_last_error", "gudni_b200_destroy",
 ]
 
@@ -73,6 +73,7 @@ def load_library():
     L.gudni_b200_sync.argtypes = [vp]
     L.gudni_b200_last_frame_ms.argtypes = [vp, c.POINTER(c.c_float)]
     L.gudni_b200_launch_count.argtypes = [vp, c.POINTER(i64)]
+    L.gudni_b200_debug_selftest.argtypes = [vp, c.c_uint64, c.c_uint64, c.POINTER(c.c_uint64)]
     L.gudni_b200_debug_enable.argtypes = [vp, i32]
     L.gudni_b200_debug_thread_counts.argtypes = [vp, vp, vp, i64, c.POINTER(i64)]
     L.gudni_b200_debug_binned.argtypes = [vp, vp, i64, c.POINTER(i64), vp, i64, c.POINTER(i64)]
@@ -256,6 +257,11 @@ class Rasterizer:
     # -- parity taps -----------------------------------------------------------------------------
     def debug_enable(self, on=True):
         self._check(self._L.gudni_b200_debug_enable(self._ctx, int(on)))
+
+    def debug_selftest(self, n=1 << 28, seed=1):
+        bad = ctypes.c_uint64()
+        self._check(self._L.gudni_b200_debug_selftest(self._ctx, n, seed, ctypes.byref(bad)))
+        return bad.value
 
     def debug_thread_counts(self):
         n = ctypes.c_int64()

@@ -200,6 +200,10 @@ int gudni_b200_launch_count(gudni_ctx* ctx, int64_t* n);
 int gudni_b200_debug_enable(gudni_ctx* ctx, int on);
 int gudni_b200_debug_thread_counts(gudni_ctx* ctx, int32_t* n_thresholds, int32_t* shape_bits,
                                    int64_t capacity, int64_t* n_threads);
+/* Device self-test of the arithmetic helpers that are not a literal transcription of the reference:
+ * the shared-reciprocal IEEE division used by `composite` is compared bit for bit with the
+ * compiler's division on `n` pseudo-random operand triples; *mismatches must come back 0. */
+int gudni_b200_debug_selftest(gudni_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
 /* Tiles and per-tile shape lists produced by the last level-2 binning, in job order. */
 int gudni_b200_debug_binned(gudni_ctx* ctx, gudni_tile* tiles, int64_t tile_capacity,
                             int64_t* n_tiles, gudni_shape* shapes, int64_t shape_capacity,

@@ -45,3 +45,10 @@ def test_empty_scene_is_background(rasterizer):
     s = scenes.fuzzy_circles(0, 300, 200, 5, 50, 1, background=(0.25, 0.5, 0.75, 1.0))
     img, stats, ref = level1_parity(rasterizer, s)
     assert np.all(img == img[0, 0])
+
+
+def test_shared_reciprocal_division_is_ieee(rasterizer):
+    """composite's three divisions share one reciprocal (raster_device.cuh div3); the result must be
+    the correctly rounded quotient, bit for bit, on every operand triple."""
+    assert rasterizer.debug_selftest(n=1 << 30, seed=0x5EED) == 0
+    assert rasterizer.debug_selftest(n=1 << 28, seed=12345) == 0
