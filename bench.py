@@ -272,7 +272,7 @@ def run_native(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "raster_tiles_kernel (+ raster_spill_kernel)", "kernel_ms": k_ms,
+                         "kernel": "raster_generate_kernel + raster_sweep_kernel (+ raster_spill_kernel), one launch each per frame", "kernel_ms": k_ms,
                          "bin_ms": float(np.mean(bin_ms)) if bin_ms else None, "algorithmic_bytes": int(a_bytes)},
             "frame": stats.as_dict() if stats is not None else None,
         }
