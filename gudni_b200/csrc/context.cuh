@@ -57,6 +57,7 @@ struct gudni_ctx {
     DevBuf spillThr, spillHdr;
     DevBuf thrStore, hdrStore, threadRecs;   // generate -> sweep hand-over
     unsigned long long storeCap = 0;
+    unsigned long long storeDemand = 0;   // thresholds the generate kernel wanted to store last frame
     int spillSlots = 0;
 
     // taps

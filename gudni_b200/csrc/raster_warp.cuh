@@ -27,7 +27,10 @@
 namespace gudni_dev {
 
 constexpr int kWarpTableCap = 128;
-constexpr int kQueueCap = 64;          // thresholds per column-thread before the HBM replay takes over
+#ifndef GUDNI_QUEUE_CAP
+#define GUDNI_QUEUE_CAP 64
+#endif
+constexpr int kQueueCap = GUDNI_QUEUE_CAP;          // thresholds per column-thread before the HBM replay takes over
 #ifndef GUDNI_QUEUE_HOT
 #define GUDNI_QUEUE_HOT 12
 #endif

@@ -61,11 +61,14 @@ int ensureFrameBuffer(gudni_ctx* ctx) {
     return devEnsure(ctx, ctx->frame, std::max<size_t>(bytes, 4));
 }
 
-// Hand-over buffers between the generate and the sweep kernel: 16 thresholds per column-thread on
-// average (threads that do not fit are replayed), one 32-byte record per thread.
+// Hand-over buffers between the generate and the sweep kernel: room for 16 thresholds per
+// column-thread or one per four pixels, whichever is more, and at least 25 % above what the previous
+// frame asked for (warps that find the store full hand their threads to the replay kernel, so an
+// undersized first frame is slow, not wrong); one 32-byte record per thread.
 int ensureHandover(gudni_ctx* ctx, int64_t totalTiles) {
     const size_t threads = (size_t)totalTiles * (size_t)ctx->spec.threads_per_tile;
-    const size_t entries = std::max<size_t>(threads * 16, (size_t)1 << 20);
+    const size_t pixels = (size_t)ctx->width * (size_t)(ctx->rowEnd - ctx->rowBegin);
+    const size_t entries = std::max({threads * 16, pixels / 4, (size_t)(ctx->storeDemand + ctx->storeDemand / 4), (size_t)1 << 20});
     GUDNI_TRY(devEnsure(ctx, ctx->thrStore, entries * 16));
     GUDNI_TRY(devEnsure(ctx, ctx->hdrStore, entries * 4));
     ctx->storeCap = std::min(ctx->thrStore.cap / 16, ctx->hdrStore.cap / 4);
@@ -371,6 +374,7 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     s.n_shape_refs = ctx->nShapes;
     s.n_thresholds = (int64_t)counters[gudni_dev::kCntThresholds];
     s.n_spilled_threads = (int64_t)counters[gudni_dev::kCntSpilled];
+    ctx->storeDemand = counters[gudni_dev::kCntStoreCursor];
     int64_t dropped = std::max<int64_t>(0, s.n_spilled_threads - ctx->spillCapacity);
     s.n_overflow_threads = (int64_t)counters[gudni_dev::kCntOverflow] + dropped;
     s.algorithmic_bytes = (int64_t)ctx->geometryBytes + 16 * ctx->nShapes + 32 * ctx->nTiles + 16 * (int64_t)ctx->nSubstances +

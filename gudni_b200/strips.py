@@ -130,14 +130,21 @@ class StripRenderer:
             torch.cuda.synchronize()
             dist.barrier()
             return
+        n = self.my_rows[1] - self.my_rows[0]
+        self.gather_strips(dist, self.rank, self.presenting, self.rows,
+                           self.strip[:n] if self.strip is not None else None, self.canvas)
+
+    @staticmethod
+    def gather_strips(dist, rank, presenting, rows, strip, canvas):
+        """Finished strips to the presenting rank: it posts one irecv per remote strip straight into
+        the canvas rows, every other rank one isend (grouped; NCCL over NVLink, or gloo in tests)."""
         ops = []
-        if self.rank == self.presenting:
-            for k, (y0, y1) in enumerate(self.rows):
-                if k != self.rank and y1 > y0:
-                    ops.append(dist.P2POp(dist.irecv, self.canvas[y0:y1], k))
-        elif self.my_rows[1] > self.my_rows[0]:
-            n = self.my_rows[1] - self.my_rows[0]
-            ops.append(dist.P2POp(dist.isend, self.strip[:n], self.presenting))
+        if rank == presenting:
+            for k, (y0, y1) in enumerate(rows):
+                if k != rank and y1 > y0:
+                    ops.append(dist.P2POp(dist.irecv, canvas[y0:y1], k))
+        elif rows[rank][1] > rows[rank][0]:
+            ops.append(dist.P2POp(dist.isend, strip, presenting))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
