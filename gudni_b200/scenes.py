@@ -180,3 +180,138 @@ def random_rectangles(n, width, height, seed, max_size=40.0, alpha=(0.2, 1.0)):
             b.circle(s, [("translate", float(x), float(y)), ("scale", float(w) / 4)], subtract=True)
             b.circle(s, [("translate", float(x), float(y)), ("scale", float(w) / 2)])
     return b.freeze()
+
+
+# ---- textured / glyph configs -----------------------------------------------
+
+def _circle_outline(transforms):
+    """Unit circle (Layout/Draw.hs:153-154) through a transformer stack given outermost first,
+    returned as curve pairs; f32 arithmetic like the harness' C++ (apply innermost first)."""
+    from .scene import unit_circle_pairs
+    pts = unit_circle_pairs().reshape(-1, 2).astype(np.float32)
+    for t in reversed(list(transforms)):
+        if t[0] == "translate":
+            pts = pts + np.array([t[1], t[2]], np.float32)
+        elif t[0] == "scale":
+            pts = pts * np.float32(t[1])
+    return pts.reshape(-1, 4).astype(np.float32)
+
+
+def synthetic_picture(width, height, seed):
+    """Stand-in for image/hero-yellow-flowers.jpg (1400x750): seeded smooth RGBA8 field with opaque
+    and translucent regions.  (Reference assets are not copied into this repo.)"""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width].astype(np.float32)
+    img = np.zeros((height, width, 4), np.uint8)
+    for c in range(3):
+        fx, fy, ph = rng.uniform(0.005, 0.05), rng.uniform(0.005, 0.05), rng.uniform(0, 6.28)
+        img[..., c] = (127.5 + 127.5 * np.sin(fx * x + fy * y + ph)).astype(np.uint8)
+    img[..., 3] = np.where((x // 37 + y // 29) % 5 == 0, 128, 255).astype(np.uint8)
+    return img
+
+
+def hsl_gradient_picture(w=200, h=200):
+    """testPict's PictureFunction (benchmarks/GudniTests.hs:272-276): hsl 0 (x/w) (y/h), RGBA8."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    s, l = x / np.float32(w), y / np.float32(h)
+    q = np.where(l < 0.5, l * (1 + s), l + s - l * s)
+    p = 2 * l - q
+
+    def comp(t):
+        t = t - np.floor(t)
+        return np.where(t < 1 / 6, p + (q - p) * 6 * t, np.where(t < 0.5, q, np.where(t < 2 / 3, p + (q - p) * 6 * (2 / 3 - t), p)))
+
+    rgb = np.stack([comp(np.full_like(l, 1 / 3)), comp(np.zeros_like(l)), comp(np.full_like(l, -1 / 3))], axis=-1)
+    out = np.empty((h, w, 4), np.uint8)
+    out[..., :3] = np.clip(np.floor(rgb * 255.0), 0, 255).astype(np.uint8)   # colorToRGBA8 truncates
+    out[..., 3] = 255
+    return out
+
+
+def picture_scene(width=640, height=480, scale=1.0, background=(0.2, 0.2, 0.2, 1.0), flowers_size=(1400, 750)):
+    """testPict (benchmarks/GudniTests.hs:271-281): a picture on `circle200 - (circle100@(100,100) +
+    circle100)`, an HSL gradient PictureFunction on a radius-200 circle, a translucent bar; the
+    whole thing optionally scaled (S3 uses x2).  Picture usages take the translation but only the
+    scale factor of an enclosing tScale (Figure/Picture.hs:113-116)."""
+    b = SceneBuilder(width, height, background, name=f"testPict-{width}x{height}-x{scale}")
+    sc = ("scale", float(scale))
+    outer = [sc, ("translate", 100.0, 50.0)]
+    flowers = b.picture(synthetic_picture(flowers_size[0], flowers_size[1], 0xF10E5))
+    s0 = b.picture_substance(flowers, (100.0, 50.0), float(scale))
+    b.shape(s0, [_circle_outline(outer + [("translate", 100.0, 100.0), ("scale", 100.0)])], subtract=True, is_picture=True)
+    b.shape(s0, [_circle_outline(outer + [("scale", 100.0)])], subtract=True, is_picture=True)
+    b.shape(s0, [_circle_outline(outer + [("scale", 200.0)])], is_picture=True)
+    gradient = b.picture(hsl_gradient_picture())
+    s1 = b.picture_substance(gradient, (100.0, 50.0), float(scale))
+    b.shape(s1, [_circle_outline(outer + [("scale", 200.0)])], is_picture=True)
+    s2 = b.solid(0.0, 0.0, 1.0, 0.2)
+    b.rectangle(s2, 40.0, 2000.0, outer)
+    return b.freeze()
+
+
+def s3(width=3840, height=2160):
+    """S3 — plots + textures at 4K: testPict x2 plus a row of solid closed curves standing in for the
+    turtle plots of examples/Plot.hs (arcs, rounded boxes, circles)."""
+    b = SceneBuilder(width, height, (0.2, 0.2, 0.2, 1.0), name=f"S3-plots-textures-{width}x{height}")
+    outer = [("scale", 2.0), ("translate", 100.0, 50.0)]
+    flowers = b.picture(synthetic_picture(1400, 750, 0xF10E5))
+    s0 = b.picture_substance(flowers, (100.0, 50.0), 2.0)
+    b.shape(s0, [_circle_outline(outer + [("translate", 100.0, 100.0), ("scale", 100.0)])], subtract=True, is_picture=True)
+    b.shape(s0, [_circle_outline(outer + [("scale", 100.0)])], subtract=True, is_picture=True)
+    b.shape(s0, [_circle_outline(outer + [("scale", 200.0)])], is_picture=True)
+    gradient = b.picture(hsl_gradient_picture())
+    s1 = b.picture_substance(gradient, (100.0, 50.0), 2.0)
+    b.shape(s1, [_circle_outline(outer + [("scale", 200.0)])], is_picture=True)
+    s2 = b.solid(0.0, 0.0, 1.0, 0.2)
+    b.rectangle(s2, 40.0, 2000.0, outer)
+    yellow = b.solid(*YELLOW, 1.0)
+    for i in range(16):   # 16-wide row of plot-like closed curves, scale 30 -> x4
+        x, y = 1000.0 + 170.0 * i, 300.0 + 90.0 * (i % 5)
+        if i % 3 == 0:
+            b.circle(yellow, [("translate", x, y), ("scale", 60.0)])
+        elif i % 3 == 1:
+            b.rectangle(yellow, 120.0, 80.0, [("translate", x, y), ("rotate", 0.03 * i)])
+        else:
+            b.circle(yellow, [("translate", x, y), ("scale", 30.0)], subtract=True)
+            b.circle(yellow, [("translate", x, y), ("scale", 70.0)])
+    return b.freeze()
+
+
+def _synthetic_glyph(rng):
+    """A glyph-like shape in the unit em box: an outer contour of 10-20 quadratic curves around the
+    centre and, half of the time, an inner counter (a hole drawn as a second outline)."""
+    outlines = []
+    for k, (r0, r1) in enumerate([(0.28, 0.45)] + ([(0.08, 0.16)] if rng.uniform() < 0.5 else [])):
+        n = int(rng.integers(5, 11))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, 2 * n))
+        rad = rng.uniform(r0, r1, 2 * n)
+        pts = np.stack([0.5 + rad * np.cos(ang) * 0.8, 0.5 + rad * np.sin(ang)], axis=1).astype(np.float32)
+        if k == 1:
+            pts = pts[::-1].copy()
+        outlines.append(pts.reshape(n, 4).astype(np.float32))   # (on, off) pairs: Outline.hs:74-77 pairPoints
+    return outlines
+
+
+def s2(width=1920, height=1080, lines=30, em=30.0, seed=0x5EED0002):
+    """S2 — examples/Paragraph.hs restated: 30 lines of glyph outlines, em = 30 px, advance 0.8 em +
+    0.2 em gaps, ONE opaque black substance for every glyph and for a radius-10-em circle to the right
+    of the text, light gray background.  No usable font ships with the image's Python stack, so the
+    glyphs are seeded synthetic outlines (SURVEY.md §8(d) fallback); 76 glyphs per line ~ 2,280."""
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder(width, height, (0.83, 0.83, 0.83, 1.0), name=f"S2-paragraph-{width}x{height}")
+    black = b.solid(0.0, 0.0, 0.0, 1.0)
+    alphabet = [_synthetic_glyph(rng) for _ in range(48)]
+    per_line = 76
+    for line in range(lines):
+        for col in range(per_line):
+            if rng.uniform() < 0.15:
+                continue   # a space
+            g = alphabet[int(rng.integers(0, len(alphabet)))]
+            ox, oy = np.float32(10.0 + col * em * 0.8), np.float32(10.0 + line * em * 1.15)
+            outs = []
+            for o in g:
+                p = o.reshape(-1, 2) * np.float32(em) + np.array([ox, oy], np.float32)
+                outs.append(p.reshape(-1, 4).astype(np.float32))
+            b.shape(black, outs)
+    b.circle(black, [("translate", 10.0 + per_line * em * 0.8 + 10 * em, 10 * em + 10.0), ("scale", 10 * em)])
+    return b.freeze()

@@ -65,3 +65,15 @@ def test_small_tile_spec(rasterizer):
         level2_parity(r, scenes.fuzzy_circles(800, 300, 260, 5, 40, 0x1234), spec=spec)
     finally:
         r.close()
+
+
+def test_picture_scene(rasterizer):
+    level2_parity(rasterizer, scenes.picture_scene(640, 480, flowers_size=(700, 375)))
+
+
+def test_s2_paragraph(rasterizer):
+    level2_parity(rasterizer, scenes.s2(1920, 1080))
+
+
+def test_s3_plots_textures_reduced(rasterizer):
+    level2_parity(rasterizer, scenes.s3(1920, 1080))

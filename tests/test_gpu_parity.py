@@ -52,3 +52,13 @@ def test_shared_reciprocal_division_is_ieee(rasterizer):
     the correctly rounded quotient, bit for bit, on every operand triple."""
     assert rasterizer.debug_selftest(n=1 << 30, seed=0x5EED) == 0
     assert rasterizer.debug_selftest(n=1 << 28, seed=12345) == 0
+
+
+def test_picture_substances(rasterizer):
+    """Texture substances (testPict): per-pixel picture lookups, subtract inside a picture substance."""
+    level1_parity(rasterizer, scenes.picture_scene(640, 480, flowers_size=(700, 375)))
+    level1_parity(rasterizer, scenes.picture_scene(900, 700, scale=2.0, flowers_size=(700, 375)))
+
+
+def test_s2_paragraph_reduced(rasterizer):
+    level1_parity(rasterizer, scenes.s2(960, 540, lines=14))

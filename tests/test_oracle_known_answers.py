@@ -157,3 +157,40 @@ def test_image_independent_of_raster_spec(spec):
     s = scenes.concentric_squares3(size=40)
     base = oracle.render(s).image
     assert np.array_equal(oracle.render(s, spec).image, base)
+
+
+def test_picture_substance_texel_lookup():
+    """readColor for a picture (Kernels.cl:1420-1441): texel = trunc(absPos / scale - translate),
+    colour = RGBA8 / 255, outside the picture transparent; pixel = trunc(colour * 255)."""
+    from gudni_b200.scene import SceneBuilder
+    rng = np.random.default_rng(3)
+    pict = rng.integers(0, 256, size=(6, 8, 4), dtype=np.uint8)
+    pict[..., 3] = 255
+    b = SceneBuilder(32, 32, (0.0, 0.0, 0.0, 1.0))
+    p = b.picture(pict)
+    s = b.picture_substance(p, translate=(2.0, 3.0), scale=2.0)
+    b.shape(s, [scenes._straight_outline([(0, 0), (30, 0), (30, 30), (0, 30)])], is_picture=True)
+    img = oracle.render(b.freeze()).image
+    for (x, y) in [(4, 6), (5, 7), (10, 9), (19, 17), (3, 6), (4, 5), (20, 6), (4, 18)]:
+        tx = int(np.trunc(F(x) / F(2.0) - F(2.0)))
+        ty = int(np.trunc(F(y) / F(2.0) - F(3.0)))
+        if 0 <= tx < 8 and 0 <= ty < 6:
+            want = tuple(int(np.trunc((F(pict[ty, tx, c]) / F(255.0)) * F(255.0))) for c in range(3))
+        else:
+            want = (0, 0, 0)   # transparent picture over the opaque black background
+        assert rgb(img, x, y)[:3] == want, (x, y, tx, ty)
+
+
+def test_oracle_matches_committed_golden_hashes():
+    """Regression pin of the oracle itself: image hashes generated by tests/golden/make_golden.py."""
+    import hashlib
+    import json
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "oracle_hashes.json")
+    golden = json.load(open(path))
+    from golden.make_golden import SCENES
+    for name, make in SCENES.items():
+        r = oracle.render(make())
+        digest = hashlib.sha256(r.image.tobytes()).hexdigest()
+        assert digest == golden[name]["sha256"], name
+        assert r.total_thresholds == golden[name]["thresholds"], name
