@@ -139,6 +139,27 @@ __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, 
     }
 }
 
+// (min y, max y) over all points of every strand of `count` shape records (`stride` bytes apart, each
+// starting with {u64 tag, u32 geo_start, u32 num_strands}); strand layout K.cl:1365-1376.
+__global__ void strand_bounds_kernel(const uint8_t* __restrict__ geometry, const uint8_t* __restrict__ records, int stride,
+                                     int count, float2* __restrict__ bounds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint4 rec = __ldg(reinterpret_cast<const uint4*>(records + (size_t)i * stride));
+    const uint8_t* strand = geometry + 16ull * rec.z;
+    for (uint32_t s = 0; s < rec.w; s++) {
+        const uint32_t size = __ldg(reinterpret_cast<const uint32_t*>(strand)) & 0xFFFFu;   // in 8-byte units
+        float lo = FLT_MAX, hi = -FLT_MAX;
+        for (uint32_t k = 1; k < size; k++) {
+            const float y = __ldg(reinterpret_cast<const float*>(strand + 8 * k + 4));
+            lo = fminf(lo, y);
+            hi = fmaxf(hi, y);
+        }
+        bounds[(size_t)(strand - geometry) >> 4] = make_float2(lo, hi);
+        strand += 8u * size;
+    }
+}
+
 // div3 against the compiler's IEEE division on pseudo-random operands (and the edge cases around
 // the fast-path window); counts bit mismatches.
 __global__ void selftest_div3_kernel(unsigned long long n, unsigned long long seed, unsigned long long* mismatches) {
@@ -171,6 +192,14 @@ __global__ void selftest_div3_kernel(unsigned long long n, unsigned long long se
 }
 
 namespace gudni_launch {
+int strandBounds(gudni_ctx* ctx, const void* geometry, const void* records, int stride, int count, float2* bounds) {
+    if (count <= 0) return GUDNI_OK;
+    strand_bounds_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(geometry),
+                                                                     static_cast<const uint8_t*>(records), stride, count, bounds);
+    ctx->launches++;
+    GUDNI_CUDA_TRY(ctx, cudaGetLastError());
+    return GUDNI_OK;
+}
 int selftestDiv3(gudni_ctx* ctx, unsigned long long n, unsigned long long seed, unsigned long long* devMismatches) {
     selftest_div3_kernel<<<148 * 8, 256, 0, ctx->stream>>>(n, seed, devMismatches);
     ctx->launches++;

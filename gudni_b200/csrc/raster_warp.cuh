@@ -214,6 +214,9 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
     uint32_t* outp = P.out + (size_t)(g.originY - P.rowOrigin) * P.width + g.originX;   // only dereferenced when active
     ulonglong2* myKey = W.recKey + lane * kSectionsPerRound;
     float* myArea = W.recArea + lane * kSectionsPerRound;
+#ifdef GUDNI_STATS
+    unsigned long long nRec = 0, nReady = 0, nPendHit = 0, nNew = 0, nSlow = 0, nRounds = 0, nFlush = 0, nLogged = 0;
+#endif
     int logLen = 0;        // entries in this lane's log
     int wrow = 0;          // pixels of the slab stored so far (rows complete in order)
     int pendingCount = 0;  // warp-uniform
@@ -252,11 +255,18 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                 st.accB += r.z * r.w;
                 st.accArea += r.w;
             }
+#ifdef GUDNI_STATS
+            if (lane == 0) nFlush++;
+            nLogged += logLen;
+#endif
             logLen = 0;
             pendingCount = 0;
             __syncwarp();
             if (!anyAlive) break;
         }
+#ifdef GUDNI_STATS
+        if (lane == 0) nRounds++;
+#endif
         // ---- (A) band boundary: close the pixel, open the next band ---------------------------------
         if (st.alive && st.ex == 1.0f) {
             if (st.ey >= st.pixelY) {   // calculatePixel's loop condition failed: the pixel is complete
@@ -330,6 +340,9 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                     const ulonglong2 k = W.cacheKey[line];
                     const bool same = k.x == key.x && k.y == key.y;
                     if (same && c.w > -999.f) out = c;                       // ready colour or pending reference
+#ifdef GUDNI_STATS
+                    nRec++; if (same && c.w > 0.f) nReady++; else if (same && c.w > -999.f) nPendHit++;
+#endif
                     else if (c.w < 0.f && c.w > -999.f) slow = true;         // line pinned by another pending stack
                     else miss = true;
                 }
@@ -346,6 +359,9 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                             W.cacheKey[line] = key;
                             W.cacheColor[line] = make_float4(0.f, 0.f, 0.f, -(float)(1 + idx));
                             out.w = -(float)(1 + idx);
+#ifdef GUDNI_STATS
+                            nNew++;
+#endif
                         } else {   // more than kPendingCap new stacks in flight: composite on the spot (rare)
                             const float4 c = denseColor(P, W, key.y, key.x, bgPremul, 0, 0);
                             out = make_float4(c.x, c.y, c.z, 1.f);
@@ -361,6 +377,9 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                     }
                 }
                 // leftovers, one after the other: already pending? else append without a cache line
+#ifdef GUDNI_STATS
+                if (slow) nSlow++;
+#endif
                 unsigned todo = __ballot_sync(full, slow);
                 while (todo) {
                     const int src = __ffs(todo) - 1;
@@ -410,6 +429,11 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
         }
         __syncwarp();
     }
+#ifdef GUDNI_STATS
+    atomicAdd(&P.counters[8], nRec); atomicAdd(&P.counters[9], nReady); atomicAdd(&P.counters[10], nPendHit);
+    atomicAdd(&P.counters[11], nNew); atomicAdd(&P.counters[12], nSlow); atomicAdd(&P.counters[13], nRounds);
+    atomicAdd(&P.counters[14], nFlush); atomicAdd(&P.counters[15], nLogged);
+#endif
     return spilled ? 1 : 0;
 }
 

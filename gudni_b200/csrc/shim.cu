@@ -52,6 +52,7 @@ FrameParams makeParams(gudni_ctx* ctx) {
     P.hdrStore = ctx->hdrStore.as<uint32_t>();
     P.storeCap = ctx->storeCap;
     P.threadRecs = ctx->threadRecs.as<gudni_dev::ThreadRec>();
+    P.strandBounds = ctx->strandBounds.as<float2>();
     return P;
 }
 
@@ -173,7 +174,7 @@ void gudni_b200_destroy(gudni_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->geometry, &ctx->substances, &ctx->pictures, &ctx->pictureUses, &ctx->shapes, &ctx->tiles,
                       &ctx->tileThreadBase, &ctx->frame, &ctx->counters, &ctx->spillList, &ctx->spillThr, &ctx->spillHdr,
                       &ctx->dbgThresholds, &ctx->dbgShapeBits, &ctx->entries, &ctx->binCounters, &ctx->thrStore, &ctx->hdrStore,
-                      &ctx->threadRecs};
+                      &ctx->threadRecs, &ctx->strandBounds};
     for (DevBuf* b : bufs)
         if (b->ptr) cudaFree(b->ptr);
     for (DevBuf& b : ctx->binWork)
@@ -298,6 +299,9 @@ int gudni_b200_raster_job(gudni_ctx* ctx, const gudni_shape* shapes, int n_shape
     ctx->nColumns += columns_allocated;
     GUDNI_TRY(ensureHandover(ctx, ctx->nTiles));
     markFirstKernel(ctx);
+    GUDNI_TRY(devEnsure(ctx, ctx->strandBounds, ctx->geometryBytes / 2 + 16));
+    GUDNI_TRY(gudni_launch::strandBounds(ctx, ctx->geometryPtr, ctx->shapes.as<gudni_shape>() + (ctx->nShapes - n_shapes),
+                                         (int)sizeof(gudni_shape), n_shapes, ctx->strandBounds.as<float2>()));
     GUDNI_TRY(gudni_launch::rasterTiles(ctx, makeParams(ctx), tileBase, n_tiles));
     ctx->rasteredTiles = ctx->nTiles;
     return GUDNI_OK;
@@ -306,6 +310,9 @@ int gudni_b200_raster_job(gudni_ctx* ctx, const gudni_shape* shapes, int n_shape
 static int rasterSceneCommon(gudni_ctx* ctx, const void* devEntries, int n_entries) {
     GUDNI_TRY(ensureFrameBuffer(ctx));
     markFirstKernel(ctx);
+    GUDNI_TRY(devEnsure(ctx, ctx->strandBounds, ctx->geometryBytes / 2 + 16));
+    GUDNI_TRY(gudni_launch::strandBounds(ctx, ctx->geometryPtr, devEntries, (int)sizeof(gudni_shape_entry), n_entries,
+                                         ctx->strandBounds.as<float2>()));
     GUDNI_TRY(gudni_bin::binScene(ctx, static_cast<const gudni_shape_entry*>(devEntries), n_entries));
     GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evBinDone, ctx->stream));
     GUDNI_TRY(ensureDebug(ctx, 0, ctx->nColumns));
@@ -364,8 +371,8 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->inFrame = false;
 #ifdef GUDNI_STATS
-    fprintf(stderr, "[stats] sections %llu hits %llu parks %llu rounds %llu evals %llu zero-area %llu\n", counters[8], counters[9],
-            counters[10], counters[11], counters[12], counters[13]);
+    fprintf(stderr, "[stats] records %llu ready-hits %llu pending-hits %llu new %llu slow %llu rounds %llu flushes %llu logged %llu\n",
+            counters[8], counters[9], counters[10], counters[11], counters[12], counters[13], counters[14], counters[15]);
 #endif
     if (binCounters[4])
         return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "a minimum-size tile lists more than 65535 shapes: unsupported by the raster kernels");
