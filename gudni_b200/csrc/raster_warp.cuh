@@ -79,14 +79,21 @@ struct LaneLog {
 
 // determineColor (K.cl:1447-1513) for a dense tile: table index = stack bit.
 static __device__ __noinline__ float4 denseColor(const FrameParams& P, const WarpScratch& W, uint64_t hi, uint64_t lo,
-                                             float4 bgPremul, int absX, int absY) {
+                                                 float4 bgPremul, int absX, int absY) {
     float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t lastId = 0xFFFFFFFFu;
+    // walk the set bits from the top, 32 bits at a time (FLO works on 32-bit registers)
+    uint32_t word = (uint32_t)(hi >> 32);
+    int wordBase = 96;
     for (;;) {
-        int bit;
-        if (hi) { const int b = 63 - __clzll((long long)hi); hi ^= (1ull << b); bit = 64 + b; }
-        else if (lo) { const int b = 63 - __clzll((long long)lo); lo ^= (1ull << b); bit = b; }
-        else return compositeOverPremul(base, bgPremul);
+        while (word == 0u) {
+            if (wordBase == 0) return compositeOverPremul(base, bgPremul);
+            wordBase -= 32;
+            word = (wordBase == 64) ? (uint32_t)hi : (wordBase == 32) ? (uint32_t)(lo >> 32) : (uint32_t)lo;
+        }
+        const int b = 31 - __clz((int)word);
+        word ^= (1u << b);
+        const int bit = wordBase + b;
         const uint32_t meta = W.meta[bit];
         const uint32_t id = meta & kMetaIdMask;
         if (id != lastId && (meta & kMetaSet)) {
