@@ -183,7 +183,7 @@ __global__ void selftest_div3_kernel(unsigned long long n, unsigned long long se
         const float d = v[3];
         if (!(d > 0.0f) || isnan(v[0]) || isnan(v[1]) || isnan(v[2]) || isnan(d)) continue;
         float qx, qy, qz;
-        div3(v[0], v[1], v[2], d, qx, qy, qz);
+        div3<true>(v[0], v[1], v[2], d, qx, qy, qz);
         const float rx = v[0] / d, ry = v[1] / d, rz = v[2] / d;
         bad += (__float_as_uint(qx) != __float_as_uint(rx)) + (__float_as_uint(qy) != __float_as_uint(ry)) +
                (__float_as_uint(qz) != __float_as_uint(rz));

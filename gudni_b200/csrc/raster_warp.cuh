@@ -106,6 +106,33 @@ static __device__ __noinline__ float4 denseColor(const FrameParams& P, const War
     }
 }
 
+// The same walk for tiles whose substances are all solid and tame (substanceIsTame): no picture
+// branch, unchecked shared-reciprocal division.  This loop is where the sweep kernel spends most of
+// its instructions, so it is kept as lean as the reference's operation order allows.
+static __device__ __noinline__ float4 denseColorTame(const WarpScratch& W, uint64_t hi, uint64_t lo, float4 bgPremul) {
+    float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t lastId = 0xFFFFFFFFu;
+    uint32_t word = (uint32_t)(hi >> 32);
+    int wordBase = 96;
+    for (;;) {
+        while (word == 0u) {
+            if (wordBase == 0) return compositeOverPremulT<false>(base, bgPremul);
+            wordBase -= 32;
+            word = (wordBase == 64) ? (uint32_t)hi : (wordBase == 32) ? (uint32_t)(lo >> 32) : (uint32_t)lo;
+        }
+        const int b = 31 - __clz((int)word);
+        word ^= (1u << b);
+        const int bit = wordBase + b;
+        const uint32_t meta = W.meta[bit];
+        const uint32_t id = meta & kMetaIdMask;
+        if (id != lastId && (meta & kMetaSet)) {
+            base = compositeOverPremulT<false>(base, W.premul[bit]);
+            if (base.w == 1.0f) return base;
+        }
+        lastId = id;
+    }
+}
+
 __device__ __forceinline__ uint32_t stackHash(uint64_t hi, uint64_t lo) {
     uint32_t t = (uint32_t)lo ^ ((uint32_t)(lo >> 32) * 0x85EBCA6Bu) ^ ((uint32_t)hi * 0xC2B2AE35u) ^
                  ((uint32_t)(hi >> 32) * 0x27D4EB2Fu);
@@ -185,16 +212,22 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
     const int lane = threadIdx.x & 31;
     const ThreadGeom g = threadGeom(P, tile, column);
     // ---- tile substance table + empty colour cache (warp-cooperative) -----------------------------
-    bool anyPicture = false;
+    bool anyPicture = false, anyWild = false;
     for (uint32_t i = lane; i < tile.shape_count; i += 32) {
         const uint32_t meta = tagMeta(__ldg(&P.shapes[tile.shape_start + i].tag));
         W.meta[i] = meta;
         anyPicture = anyPicture || (meta & kMetaPicture);
-        W.premul[i] = (meta & kMetaPicture) ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                            : premultiply(__ldg(P.substances + (meta & kMetaIdMask)));
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(meta & kMetaPicture)) {
+            c = __ldg(P.substances + (meta & kMetaIdMask));
+            anyWild = anyWild || !substanceIsTame(c);
+            c = premultiply(c);
+        }
+        W.premul[i] = c;
     }
     // a picture's colour depends on the pixel, so stacks are only a valid key without pictures
     const bool cacheable = !__any_sync(full, anyPicture);
+    const bool tame = cacheable && !__any_sync(full, anyWild) && substanceIsTame(P.background);
     for (int i = lane; i < kColorCacheLines; i += 32) W.cacheColor[i] = make_float4(0.f, 0.f, 0.f, -1000.f);
     // ---- the thread's sorted queue and initial stack, from the generate kernel ------------------------
     const ThreadRec rec = P.threadRecs[(size_t)unit * 32 + lane];
@@ -236,7 +269,7 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                 const int p = p0 + lane;
                 if (p < pendingCount) {
                     const ulonglong2 key = W.pendKey[p];
-                    const float4 c = denseColor(P, W, key.y, key.x, bgPremul, 0, 0);
+                    const float4 c = tame ? denseColorTame(W, key.y, key.x, bgPremul) : denseColor(P, W, key.y, key.x, bgPremul, 0, 0);
                     W.pendColor[p] = c;
                     // un-pin: the line that references this entry (if it got one) now holds the colour
                     const uint32_t line = stackHash(key.y, key.x);

@@ -17,7 +17,18 @@ for i,l in enumerate(src,1):
 marks.sort()
 def phase(fname, line):
     if fname.endswith("raster_warp.cuh"):
-        return "warp.color" if line < 70 else "warp.driver"
+        # anchors found by scanning the source for the section comments of sweepWarp
+        wsrc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gudni_b200/csrc/raster_warp.cuh")).read().splitlines()
+        anchors = []
+        for i, l in enumerate(wsrc, 1):
+            for key, name in (("float4 denseColor(", "warp.color"), ("uint32_t stackHash(", "warp.hash"), ("int generateWarp(", "warp.generate"),
+                              ("int sweepWarp(", "warp.setup"), ("// ---- flush", "warp.flush"), ("// ---- (A)", "warp.A-boundary"),
+                              ("// ---- (B)", "warp.B-sections"), ("// ---- (C)", "warp.C-resolve"), ("// ---- (D)", "warp.D-accumulate")):
+                if key in l: anchors.append((i, name))
+        ph = "warp.other"
+        for ln, name in anchors:
+            if ln <= line: ph = name
+        return ph
     if fname.endswith("raster_kernels.cu"): return "kernel"
     p="other"
     for ln,v in marks:
