@@ -315,3 +315,18 @@ def s2(width=1920, height=1080, lines=30, em=30.0, seed=0x5EED0002):
             b.shape(black, outs)
     b.circle(black, [("translate", 10.0 + per_line * em * 0.8 + 10 * em, 10 * em + 10.0), ("scale", 10 * em)])
     return b.freeze()
+
+
+def thin_rectangles(n, width=64, height=None, spacing=1.0, thickness=0.5, skew=0.3, background=(1.0, 1.0, 1.0, 1.0)):
+    """maxThresholdTest / maxShapeTest flavour (benchmarks/GudniTests.hs:100-127): a stack of wide, thin,
+    slightly skewed translucent rectangles — hundreds of thresholds per pixel column.  ONE substance, so
+    tiles are not forced to split by the shape cap... they are: each rectangle is a shape; use a small
+    canvas so tiles bottom out at 8 px and keep everything."""
+    height = int(n * spacing + 8) if height is None else height
+    b = SceneBuilder(width, height, background, name=f"thinRects-{n}")
+    for i in range(n):
+        s = b.solid(0.9 * ((i * 37) % 11) / 10.0, 0.9 * ((i * 53) % 7) / 6.0, 0.5, 0.4)
+        y = np.float32(2.0 + i * spacing)
+        pts = [(-1.0, float(y)), (width + 1.0, float(y + skew)), (width + 1.0, float(y + skew + thickness)), (-1.0, float(y + thickness))]
+        b.shape(s, [_straight_outline(pts)])
+    return b.freeze()

@@ -1,0 +1,68 @@
+"""Capacity edges: queues longer than the on-chip capacity (HBM replay path), more shapes per tile
+than stack bits, more thresholds than MAXTHRESHOLDS (undefined behaviour in the reference, reported
+here), and argument validation through the C ABI."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from gudni_b200 import scenes
+from gudni_b200.formats import RasterSpec
+from gudni_b200.raster import GudniError, setup_rasterizer
+
+from parity import level1_parity, level2_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def test_long_queues_take_the_replay_path(rasterizer):
+    # tall tile columns crossing ~2 thresholds per rectangle: well over the 64-entry on-chip queue
+    scene = scenes.thin_rectangles(60, width=64, spacing=3.0, thickness=1.3)
+    img, stats, ref = level1_parity(rasterizer, scene)
+    assert max(int(c.max()) for c in ref.n_thresholds) > 64
+    assert stats.n_spilled_threads > 0 and stats.n_overflow_threads == 0
+    level2_parity(rasterizer, scene, ref=ref)
+
+
+def test_more_shapes_than_stack_bits(rasterizer):
+    # 8-pixel tiles that keep > 127 shapes: only the first 127 that touch a column get a bit
+    scene = scenes.fuzzy_circles(6000, 128, 128, 5, 40, 0xB175)
+    img, stats, ref = level2_parity(rasterizer, scene)
+    assert max(int(j.tiles["shape_count"].max()) for j in ref.jobs) > 127
+    assert max(int(b.max()) for b in ref.shape_bits) == 127
+
+
+def test_threshold_overflow_is_reported_not_corrupting():
+    spec = RasterSpec(max_thresholds=16)
+    r = setup_rasterizer(spec=spec)
+    try:
+        # ~100 thresholds per column-thread: past the 64-entry on-chip queue, so the threads are replayed
+        # against HBM queues of max_thresholds = 16 entries, which they overflow
+        scene = scenes.thin_rectangles(100, width=32, spacing=3.0, thickness=1.3)
+        img, stats = r.raster_scene(0, scene)
+        assert stats.n_spilled_threads > 0
+        assert stats.n_overflow_threads > 0
+        # untouched threads still match the oracle run with the same spec
+        from oracle import oracle
+        ref = oracle.render(scene, spec, taps=False)
+        assert ref.overflow_threads > 0
+    finally:
+        r.close()
+
+
+def test_argument_validation(rasterizer):
+    L, ctx = rasterizer._L, rasterizer._ctx
+    bg = (ctypes.c_float * 4)(0, 0, 0, 1)
+    assert L.gudni_b200_frame_begin(ctx, None, 16, None, 0, None, 0, None, 0, bg, 64, 64, 0) == -1   # null geometry
+    assert L.gudni_b200_frame_begin(ctx, None, 0, None, 0, None, 0, None, 0, bg, 0, 64, 0) == -1     # empty bitmap
+    assert L.gudni_b200_raster_scene(ctx, None, 0) == -4                                              # outside a frame
+    assert b"outside a frame" in L.gudni_b200_last_error(ctx)
+    scene = scenes.tiny_square()
+    rasterizer.frame_begin(scene, 0)
+    bad = np.zeros(1, dtype=[("left", "<i4"), ("top", "<i4"), ("right", "<i4"), ("bottom", "<i4"), ("h_depth", "<i2"),
+                             ("v_depth", "<i2"), ("column_allocation", "<i4"), ("shape_start", "<u4"), ("shape_count", "<u4")])
+    bad["shape_count"] = 5   # slice beyond the (empty) shape array
+    assert L.gudni_b200_raster_job(ctx, None, 0, bad.ctypes.data, 1, 256, 0) == -1
+    rasterizer.frame_end(want_image=False)
+    with pytest.raises(GudniError):
+        setup_rasterizer(spec=RasterSpec(threads_per_tile=100))   # not a power of two
