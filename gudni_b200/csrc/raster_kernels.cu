@@ -34,7 +34,10 @@ __device__ __forceinline__ void registerSpill(const FrameParams& P, int tileInde
         P.spillList[slot] = ((unsigned long long)tileIndex << 32) | (unsigned long long)column;
 }
 
-__global__ void __launch_bounds__(kGenWarpsPerCta * 32) raster_generate_kernel(const FrameParams P, int tileBase, int nTiles) {
+#ifndef GUDNI_GEN_MIN_CTAS
+#define GUDNI_GEN_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(kGenWarpsPerCta * 32, GUDNI_GEN_MIN_CTAS) raster_generate_kernel(const FrameParams P, int tileBase, int nTiles) {
     __shared__ GenScratch scratch[kGenWarpsPerCta];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -36,7 +36,7 @@ constexpr int kQueueCap = GUDNI_QUEUE_CAP;          // thresholds per column-thr
 #endif
 constexpr int kQueueHot = GUDNI_QUEUE_HOT;           // of which in shared memory (sweep kernel)
 #ifndef GUDNI_GEN_QUEUE_HOT
-#define GUDNI_GEN_QUEUE_HOT 16
+#define GUDNI_GEN_QUEUE_HOT 8
 #endif
 constexpr int kGenQueueHot = GUDNI_GEN_QUEUE_HOT;       // ... (generate kernel)
 #ifndef GUDNI_CACHE_LINES
