@@ -224,6 +224,12 @@ def run_native(args, rank, world, local_rank):
     rows = strips.my_rows[1] - strips.my_rows[0]
     d2h = 4 * scene.width * (scene.height if world == 1 else 0)
     host_img = np.empty((scene.height, scene.width), dtype=np.uint32) if rank == 0 else None
+    # the base contract's e2e leg copies from / to pinned host memory: page-lock the caller-side buffers
+    # once (gudni_b200_host_register), as a client with long-lived Piles would
+    pinned = [a for a in (scene.geometry, scene.substances, scene.entries, scene.picture_bytes, host_img)
+              if a is not None and a.nbytes and world == 1]
+    for a in pinned:
+        r.host_register(a)
     n_e2e = max(3, min(args.steps, 10))
     for i in range(2 + n_e2e):
         barrier()
@@ -239,6 +245,8 @@ def run_native(args, rank, world, local_rank):
         barrier()
         if i >= 2:
             e2e_times.append(time.perf_counter() - t0)
+    for a in pinned:
+        r.host_unregister(a)
     t_e2e = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)

@@ -480,6 +480,19 @@ int gudni_b200_download(gudni_ctx* ctx, void* host_dst, const void* dev_src, siz
     GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return GUDNI_OK;
 }
+int gudni_b200_host_register(gudni_ctx* ctx, void* host_ptr, size_t bytes) {
+    if (!ctx || !host_ptr || !bytes) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    return GUDNI_OK;
+}
+int gudni_b200_host_unregister(gudni_ctx* ctx, void* host_ptr) {
+    if (!ctx || !host_ptr) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaHostUnregister(host_ptr));
+    return GUDNI_OK;
+}
 int gudni_b200_sync(gudni_ctx* ctx) {
     if (!ctx) return GUDNI_ERR_ARGUMENT;
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "gudni_b200_init", "gudni_b200_frame_begin", "gudni_b200_frame_strip", "gudni_b200_raster_job",
     "gudni_b200_raster_scene", "gudni_b200_frame_end", "gudni_b200_frame_device_ptr", "gudni_b200_frame_target",
     "gudni_b200_ipc_export_frame", "gudni_b200_ipc_open", "gudni_b200_ipc_close", "gudni_b200_device_alloc",
-    "gudni_b200_device_free", "gudni_b200_upload", "gudni_b200_download", "gudni_b200_frame_begin_device",
+    "gudni_b200_device_free", "gudni_b200_host_register", "gudni_b200_host_unregister", "gudni_b200_upload", "gudni_b200_download", "gudni_b200_frame_begin_device",
     "gudni_b200_raster_scene_device", "gudni_b200_sync", "gudni_b200_last_frame_ms", "gudni_b200_launch_count",
     "gudni_b200_set_stream", "gudni_b200_debug_selftest", "gudni_b200_debug_enable", "gudni_b200_debug_thread_counts", "gudni_b200_debug_binned",
     "gudni_b200_last_error", "gudni_b200_destroy",
@@ -70,6 +70,8 @@ def load_library():
     L.gudni_b200_device_free.argtypes = [vp, vp]
     L.gudni_b200_upload.argtypes = [vp, vp, vp, sz]
     L.gudni_b200_download.argtypes = [vp, vp, vp, sz]
+    L.gudni_b200_host_register.argtypes = [vp, vp, sz]
+    L.gudni_b200_host_unregister.argtypes = [vp, vp]
     L.gudni_b200_sync.argtypes = [vp]
     L.gudni_b200_last_frame_ms.argtypes = [vp, c.POINTER(c.c_float)]
     L.gudni_b200_launch_count.argtypes = [vp, c.POINTER(i64)]
@@ -240,6 +242,15 @@ class Rasterizer:
     def set_stream(self, cuda_stream):
         """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream) or None."""
         self._check(self._L.gudni_b200_set_stream(self._ctx, ctypes.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def host_register(self, array):
+        """Page-lock a numpy array that will be passed again and again (see gudni_b200_host_register)."""
+        if array.nbytes:
+            self._check(self._L.gudni_b200_host_register(self._ctx, array.ctypes.data, array.nbytes))
+
+    def host_unregister(self, array):
+        if array.nbytes:
+            self._check(self._L.gudni_b200_host_unregister(self._ctx, array.ctypes.data))
 
     def sync(self):
         self._check(self._L.gudni_b200_sync(self._ctx))

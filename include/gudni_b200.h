@@ -186,6 +186,13 @@ int gudni_b200_frame_begin_device(gudni_ctx* ctx,
                                   const float background_rgba[4],
                                   int width, int height, int frame_number);
 int gudni_b200_raster_scene_device(gudni_ctx* ctx, const void* dev_entries, int n_entries);
+/* Optional: page-lock a caller-owned host buffer that stays at the same address across frames (a
+ * Haskell `Pile`'s storage, the SDL texture) so the copies in frame_begin / raster_scene / frame_end run
+ * as direct DMA instead of going through the driver's staging buffer.  Must be unregistered before the
+ * buffer is freed or reallocated.  (The reference got the same effect from CL_MEM_USE_HOST_PTR,
+ * OpenCL/Instances.hs:39-43.) */
+int gudni_b200_host_register(gudni_ctx* ctx, void* host_ptr, size_t bytes);
+int gudni_b200_host_unregister(gudni_ctx* ctx, void* host_ptr);
 /* Waits for all queued work of the context. */
 int gudni_b200_sync(gudni_ctx* ctx);
 /* Milliseconds of device time between the first and last kernel of the last frame. */
