@@ -181,6 +181,10 @@ def run_native(args, rank, world, local_rank):
     r.set_stream(stream.cuda_stream)
     strips = StripRenderer(r, scene, rank, world, dist, mode=args.gather)
     dscene = DeviceScene(r, scene, entries=strips.entries)
+    pipelined = world > 1 and args.gather == "nccl" and args.pipeline
+    if pipelined:
+        strips.prepare_chunks(dscene.put_entries, chunk_rows=args.chunk_rows)
+    render = (lambda f: strips.render_pipelined(f, dscene)) if pipelined else (lambda f: strips.render(f, dscene))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -190,8 +194,48 @@ def run_native(args, rank, world, local_rank):
             torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM, frame left in HBM -----------------------------------------
+    single = None
+    if world > 1:
+        # the same workload on ONE GPU, measured by rank 0 in this run, so the strong-scaling ratio
+        # can be read off this line alone (bench.py --gpus 1 measures the 4K scene, not this one)
+        if rank == 0:
+            solo = StripRenderer(r, scene, 0, 1, None)
+            dsolo = DeviceScene(r, scene)
+            for i in range(2):
+                solo.render(i, dsolo)
+            t = []
+            for i in range(3):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); solo.render(2 + i, dsolo); e1.record(stream)
+                torch.cuda.synchronize()
+                t.append(e0.elapsed_time(e1))
+            single = {"ms_per_step": float(np.mean(t)), "value": 1e3 / float(np.mean(t)), "unit": "frames/s"}
+            solo.close(); dsolo.free(); del solo
+        barrier()
     for i in range(args.warmup):
-        strips.render(i, dscene)
+        render(i)
+    if world > 1 and args.gather == "nccl" and not args.no_rebalance:
+        # feedback partition (contiguous tile-row strips stay): two rounds of "measure every rank's strip,
+        # cut the canvas again so the estimated times are equal"; the presenting rank is charged for the
+        # gather it receives
+        from gudni_b200.strips import rebalance_rows
+        for it in range(2):
+            st = getattr(strips, "last_stats", None)
+            mine = torch.tensor([st.ms_raster + st.ms_bin if st is not None else 0.0], dtype=torch.float64, device="cuda")
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            times = [float(x.item()) for x in allr]
+            gather_ms = 4.0 * scene.width * scene.height * (world - 1) / world / 700e9 * 1e3
+            new_rows = rebalance_rows(strips.rows, times, scene.height, r.spec.max_tile_size, 0, gather_ms)
+            if new_rows == strips.rows:
+                break
+            strips.close(); dscene.free()
+            strips = StripRenderer(r, scene, rank, world, dist, mode=args.gather, rows=new_rows)
+            dscene = DeviceScene(r, scene, entries=strips.entries)
+            render = lambda f: strips.render(f, dscene)
+            for i in range(2):
+                render(i)
     launches0 = r.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -201,7 +245,7 @@ def run_native(args, rank, world, local_rank):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        strips.render(args.warmup + i, dscene)
+        render(args.warmup + i)
         e1.record(stream)
         barrier()
         step_ms.append(e0.elapsed_time(e1))
@@ -211,6 +255,13 @@ def run_native(args, rank, world, local_rank):
             bin_ms.append(st.ms_bin)
     clocks = sampler.stop()
     launches = r.launch_count() - launches0
+    per_rank = None
+    if dist is not None:
+        mine = torch.tensor([float(np.mean(raster_ms)) if raster_ms else 0.0, float(np.mean(bin_ms)) if bin_ms else 0.0],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(x[0]), 3), round(float(x[1]), 3)] for x in allr]
     t_dev = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -223,7 +274,8 @@ def run_native(args, rank, world, local_rank):
            strips.entries.nbytes)
     rows = strips.my_rows[1] - strips.my_rows[0]
     d2h = 4 * scene.width * (scene.height if world == 1 else 0)
-    host_img = np.empty((scene.height, scene.width), dtype=np.uint32) if rank == 0 else None
+    host_img = np.empty((scene.height, scene.width), dtype=np.uint32) if (rank == 0 and world == 1) else None
+    pinned_canvas = torch.empty((scene.height, scene.width), dtype=torch.int32, pin_memory=True) if (rank == 0 and world > 1) else None
     # the base contract's e2e leg copies from / to pinned host memory: page-lock the caller-side buffers
     # once (gudni_b200_host_register), as a client with long-lived Piles would
     pinned = [a for a in (scene.geometry, scene.substances, scene.entries, scene.picture_bytes, host_img)
@@ -240,7 +292,8 @@ def run_native(args, rank, world, local_rank):
         else:
             canvas = strips.render(i, None)
             if rank == 0:
-                host_img[...] = canvas.cpu().numpy().view(np.uint32)
+                pinned_canvas.copy_(canvas, non_blocking=True)
+                torch.cuda.synchronize()
                 d2h = 4 * scene.width * scene.height
         barrier()
         if i >= 2:
@@ -271,7 +324,7 @@ def run_native(args, rank, world, local_rank):
                        "spec": "G=256 MAXT=1024 maxStrandsPerTile=1022 MAXSHAPE=127",
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": "1 GPU, whole frame" if world == 1 else
-                       f"{world} tile-row strips, gather={args.gather}",
+                       f"{world} tile-row strips, gather={args.gather}" + (f", pipelined in chunks of {args.chunk_rows} rows" if pipelined else ""),
                        "strips": strips.rows if world > 1 else None},
             "mpixel_per_s": scene.width * scene.height * value / 1e6,
             "clocks": clocks,
@@ -284,6 +337,11 @@ def run_native(args, rank, world, local_rank):
                          "bin_ms": float(np.mean(bin_ms)) if bin_ms else None, "algorithmic_bytes": int(a_bytes)},
             "frame": stats.as_dict() if stats is not None else None,
         }
+        if per_rank is not None:
+            line["per_rank_raster_bin_ms"] = per_rank
+        if single is not None:
+            line["single_gpu_same_workload"] = single
+            line["speedup_vs_single_gpu"] = value / single["value"]
         if world == 1 and not args.no_cpu_baseline:
             run, desc = oracle_frame_sampler(scene, budget_s=10.0)
             t = float(np.mean([run() for _ in range(2)]))
@@ -307,6 +365,11 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep the area-based strip partition")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="N > 1: send the strip chunk by chunk while rendering the next chunk (measured slower on S5: "
+                         "a 256-row chunk cannot fill a B200, see DESIGN.md §5)")
+    ap.add_argument("--chunk-rows", type=int, default=512, help="N > 1: rows per pipelined chunk (multiple of 256)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

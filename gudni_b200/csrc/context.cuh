@@ -56,6 +56,7 @@ struct gudni_ctx {
     int spillCapacity = 0;
     DevBuf spillThr, spillHdr;
     DevBuf thrStore, hdrStore, threadRecs;   // generate -> sweep hand-over
+    DevBuf tileOrder;                        // tiles of a launch by decreasing shape count
     DevBuf strandBounds;                     // per-strand y range, geometry_bytes / 16 entries
     unsigned long long storeCap = 0;
     unsigned long long storeDemand = 0;   // thresholds the generate kernel wanted to store last frame

@@ -55,20 +55,22 @@ __global__ void __launch_bounds__(kGenWarpsPerCta * 32, GUDNI_GEN_MIN_CTAS) rast
         if (lane == 0) unit = atomicAdd(workCounter, 1u);
         unit = __shfl_sync(full, unit, 0);
         if (unit >= totalUnits) break;
-        const int tileIndex = tileBase + (int)(unit >> warpShift);
-        const int column = (int)((unit & ((1u << warpShift) - 1u)) << 5) + lane;
+        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> warpShift)];
+        const unsigned warpInTile = unit & ((1u << warpShift) - 1u);
+        const int column = (int)(warpInTile << 5) + lane;
+        const unsigned recUnit = ((unsigned)tileIndex << warpShift) + warpInTile;   // thread records are indexed by tile, not by hand-out order
         const gudni_tile tile = P.tiles[tileIndex];
         int generated = -1;
         int failed = 0;
         if (tile.shape_count <= denseCap) {
-            failed = generateWarp(P, q, tile, tileIndex, (unsigned)tileBase * (1u << warpShift) + unit, column, generated);
+            failed = generateWarp(P, q, tile, tileIndex, recUnit, column, generated);
         } else {
             // a tile that stopped splitting at the 8-pixel floor with more shapes than stack bits:
             // its threads take the lane-private replay path (bit -> shape table, HBM queue)
             const ThreadGeom g = threadGeom(P, tile, column);
             ThreadRec rec{};
             rec.count = kRecInactive;
-            P.threadRecs[((size_t)tileBase * (1u << warpShift) + unit) * 32 + lane] = rec;
+            P.threadRecs[(size_t)recUnit * 32 + lane] = rec;
             failed = g.active ? 1 : 0;
         }
         // statistics: thresholds of lanes that completed here (replayed lanes are counted by the replay)
@@ -100,14 +102,16 @@ __global__ void __launch_bounds__(kSweepWarpsPerCta * 32) raster_sweep_kernel(co
         if (lane == 0) unit = atomicAdd(workCounter, 1u);
         unit = __shfl_sync(full, unit, 0);
         if (unit >= totalUnits) break;
-        const int tileIndex = tileBase + (int)(unit >> warpShift);
-        const int column = (int)((unit & ((1u << warpShift) - 1u)) << 5) + lane;
+        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> warpShift)];
+        const unsigned warpInTile = unit & ((1u << warpShift) - 1u);
+        const int column = (int)(warpInTile << 5) + lane;
+        const unsigned recUnit = ((unsigned)tileIndex << warpShift) + warpInTile;
         const gudni_tile tile = P.tiles[tileIndex];
         if (tile.shape_count > denseCap) continue;   // replayed lane-privately
-        const int failed = sweepWarp(P, W, q, log, tile, (unsigned)tileBase * (1u << warpShift) + unit, column);
+        const int failed = sweepWarp(P, W, q, log, tile, recUnit, column);
         if (failed) {
             // its thresholds were counted by the generate kernel; the replay counts them again
-            const ThreadRec rec = P.threadRecs[((size_t)tileBase * (1u << warpShift) + unit) * 32 + lane];
+            const ThreadRec rec = P.threadRecs[(size_t)recUnit * 32 + lane];
             atomicAdd(&P.counters[kCntThresholds], 0ull - (unsigned long long)rec.count);
             registerSpill(P, tileIndex, column);
         }
@@ -139,6 +143,28 @@ __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, 
         bool ok = rasterThread(P, sTable, 0u, g, q, P.tileThreadBase[tileIndex] + column, generated);
         if (generated > 0) atomicAdd(&P.counters[kCntThresholds], (unsigned long long)generated);
         if (!ok) atomicAdd(&P.counters[kCntOverflow], 1ull);
+    }
+}
+
+// Counting sort of the launch's tiles by shape count, descending (one CTA; 256 bins, counts >= 255
+// share the first bin).  Longest-processing-time-first order for the persistent kernels.
+__global__ void __launch_bounds__(1024) tile_order_kernel(const gudni_tile* __restrict__ tiles, int tileBase, int nTiles,
+                                                          uint32_t* __restrict__ order) {
+    __shared__ unsigned int bins[256];
+    __shared__ unsigned int starts[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) bins[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nTiles; i += blockDim.x)
+        atomicAdd(&bins[255u - min(tiles[tileBase + i].shape_count, 255u)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0;
+        for (int b = 0; b < 256; b++) { starts[b] = acc; acc += bins[b]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nTiles; i += blockDim.x) {
+        const unsigned int b = 255u - min(tiles[tileBase + i].shape_count, 255u);
+        order[tileBase + atomicAdd(&starts[b], 1u)] = (uint32_t)(tileBase + i);
     }
 }
 
@@ -230,6 +256,8 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& P, int tileBase, int nTiles) 
     const long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
     const int genGrid = (int)std::min<long long>((long long)genCtasPerSm * numSms, (units + kGenWarpsPerCta - 1) / kGenWarpsPerCta);
     const int sweepGrid = (int)std::min<long long>((long long)sweepCtasPerSm * numSms, (units + kSweepWarpsPerCta - 1) / kSweepWarpsPerCta);
+    tile_order_kernel<<<1, 1024, 0, ctx->stream>>>(P.tiles, tileBase, nTiles, const_cast<uint32_t*>(P.tileOrder));
+    ctx->launches++;
     raster_generate_kernel<<<genGrid, kGenWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
     raster_sweep_kernel<<<sweepGrid, kSweepWarpsPerCta * 32, sweepSmem, ctx->stream>>>(P, tileBase, nTiles);
     ctx->launches += 2;

@@ -53,6 +53,7 @@ FrameParams makeParams(gudni_ctx* ctx) {
     P.storeCap = ctx->storeCap;
     P.threadRecs = ctx->threadRecs.as<gudni_dev::ThreadRec>();
     P.strandBounds = ctx->strandBounds.as<float2>();
+    P.tileOrder = ctx->tileOrder.as<uint32_t>();
     return P;
 }
 
@@ -74,6 +75,7 @@ int ensureHandover(gudni_ctx* ctx, int64_t totalTiles) {
     GUDNI_TRY(devEnsure(ctx, ctx->hdrStore, entries * 4));
     ctx->storeCap = std::min(ctx->thrStore.cap / 16, ctx->hdrStore.cap / 4);
     GUDNI_TRY(devEnsure(ctx, ctx->threadRecs, std::max<size_t>(threads, 32) * sizeof(gudni_dev::ThreadRec)));
+    GUDNI_TRY(devEnsure(ctx, ctx->tileOrder, (size_t)std::max<int64_t>(totalTiles, 1) * 4, (size_t)ctx->rasteredTiles * 4));
     return GUDNI_OK;
 }
 
@@ -174,7 +176,7 @@ void gudni_b200_destroy(gudni_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->geometry, &ctx->substances, &ctx->pictures, &ctx->pictureUses, &ctx->shapes, &ctx->tiles,
                       &ctx->tileThreadBase, &ctx->frame, &ctx->counters, &ctx->spillList, &ctx->spillThr, &ctx->spillHdr,
                       &ctx->dbgThresholds, &ctx->dbgShapeBits, &ctx->entries, &ctx->binCounters, &ctx->thrStore, &ctx->hdrStore,
-                      &ctx->threadRecs, &ctx->strandBounds};
+                      &ctx->threadRecs, &ctx->strandBounds, &ctx->tileOrder};
     for (DevBuf* b : bufs)
         if (b->ptr) cudaFree(b->ptr);
     for (DevBuf& b : ctx->binWork)

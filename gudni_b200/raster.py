@@ -124,6 +124,10 @@ class DeviceScene:
         self._bufs.append(p)
         return p
 
+    def put_entries(self, entries):
+        """Upload one more shape-entry array (e.g. the entries of one chunk of a strip)."""
+        return self._put(entries), len(entries)
+
     def free(self):
         for p in self._bufs:
             self.r._L.gudni_b200_device_free(self.r._ctx, p)

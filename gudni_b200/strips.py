@@ -40,16 +40,43 @@ def partition_rows(scene, n_ranks, tile_rows=256):
     return [(bounds[k] * tile_rows, min(bounds[k + 1] * tile_rows, scene.height)) for k in range(n_ranks)]
 
 
+def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenting_extra_ms=0.0):
+    """Feedback partition: given the strips of the last frame and the time each rank spent on its strip,
+    assume cost is uniform inside a strip, and cut the canvas again so that every rank gets the same
+    estimated time (the presenting rank is charged `presenting_extra_ms` for receiving the others)."""
+    n_rows = (height + tile_rows - 1) // tile_rows
+    cost = np.zeros(n_rows)
+    for (y0, y1), t in zip(rows, times_ms):
+        a, b = y0 // tile_rows, (y1 + tile_rows - 1) // tile_rows
+        if b > a:
+            cost[a:b] = max(t, 1e-3) / (b - a)
+    n = len(rows)
+    total = cost.sum() + presenting_extra_ms
+    target = total / n
+    bounds = [0]
+    acc = 0.0
+    for k in range(n - 1):
+        want = target - (presenting_extra_ms if k == presenting else 0.0)
+        i = bounds[-1]
+        got = 0.0
+        while i < n_rows - (n - 1 - k) and (got + cost[i] * 0.5 < want or i == bounds[-1]):
+            got += cost[i]
+            i += 1
+        bounds.append(i)
+    bounds.append(n_rows)
+    return [(bounds[k] * tile_rows, min(bounds[k + 1] * tile_rows, height)) for k in range(n)]
+
+
 class StripRenderer:
     """Per-rank driver.  `dist` is torch.distributed (already initialised) or None for one GPU."""
 
-    def __init__(self, rasterizer, scene, rank=0, world=1, dist=None, mode="nccl", presenting_rank=0):
+    def __init__(self, rasterizer, scene, rank=0, world=1, dist=None, mode="nccl", presenting_rank=0, rows=None):
         import torch
         self.torch = torch
         self.r, self.scene, self.rank, self.world, self.dist = rasterizer, scene, rank, world, dist
         self.mode = mode if world > 1 else "local"
         self.presenting = presenting_rank
-        self.rows = partition_rows(scene, world, rasterizer.spec.max_tile_size)
+        self.rows = rows if rows is not None else partition_rows(scene, world, rasterizer.spec.max_tile_size)
         while len(self.rows) < world:
             self.rows.append((scene.height, scene.height))   # more ranks than tile rows: idle ranks
         self.my_rows = self.rows[rank]
@@ -88,6 +115,45 @@ class StripRenderer:
             buf = (ctypes.c_ubyte * 64).from_buffer_copy(raw)
             self.r._check(self.r._L.gudni_b200_ipc_open(self.r._ctx, buf, ctypes.byref(p)))
             self._peer_canvas = p.value
+
+    # -- pipelined variant: chunks of the strip are sent while the next chunk is being rasterized -------
+    def prepare_chunks(self, dscene_factory, chunk_rows=None):
+        """Split this rank's strip into chunks of whole tile rows; `dscene_factory(entries)` uploads a
+        chunk's shape entries and returns (device pointer, count)."""
+        tile = self.r.spec.max_tile_size
+        chunk_rows = chunk_rows or tile
+        self.chunks = []
+        for k, (y0, y1) in enumerate(self.rows):
+            parts = [(a, min(a + chunk_rows, y1)) for a in range(y0, y1, chunk_rows)]
+            self.chunks.append(parts)
+        self.chunk_entries = []
+        for (a, b) in self.chunks[self.rank]:
+            self.chunk_entries.append(dscene_factory(self.scene.subset_rows(a, b)))
+
+    def render_pipelined(self, frame, dscene):
+        """Like render(), but the strip goes out chunk by chunk: NCCL carries chunk c to the presenting
+        rank while chunk c+1 is in the raster kernels, so only the last chunk's transfer is exposed."""
+        r, dist = self.r, self.dist
+        reqs = []
+        if self.rank == self.presenting:
+            r.frame_target(self.canvas.data_ptr(), 0)
+            for k, parts in enumerate(self.chunks):
+                if k == self.rank:
+                    continue
+                for (a, b) in parts:
+                    reqs.append(dist.irecv(self.canvas[a:b], k))
+        else:
+            r.frame_target(self.strip.data_ptr(), self.my_rows[0])
+        for (a, b), (dev_entries, n) in zip(self.chunks[self.rank], self.chunk_entries):
+            r.frame_begin_device(dscene, frame)
+            r.frame_strip(a, b)
+            r.raster_entries_device(dev_entries, n)
+            _, self.last_stats = r.frame_end(want_image=False)
+            if self.rank != self.presenting:
+                reqs.append(dist.isend(self.strip[a - self.my_rows[0]: b - self.my_rows[0]], self.presenting))
+        for q in reqs:
+            q.wait()
+        return self.canvas
 
     def close(self):
         if self._peer_canvas:
