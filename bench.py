@@ -342,6 +342,26 @@ def run_native(args, rank, world, local_rank):
         if single is not None:
             line["single_gpu_same_workload"] = single
             line["speedup_vs_single_gpu"] = value / single["value"]
+        if world == 1 and args.workload == "S4" and not args.no_also:
+            # BASELINE.md §3 asks for both readings of "100k": S4 (100k shapes, the value above) and S4b
+            # (6,250 circles = exactly 100k curves); same timing method, not part of `value`
+            sb = make_scene("S4b")
+            sr = StripRenderer(r, sb, 0, 1, None)
+            db = DeviceScene(r, sb)
+            for i in range(3):
+                sr.render(i, db)
+            tb = []
+            for i in range(10):
+                flush.fill_(i & 0xFF)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); sr.render(3 + i, db); e1.record(stream)
+                torch.cuda.synchronize()
+                tb.append(e0.elapsed_time(e1))
+            line["also"] = {"S4b": {"workload": WORKLOADS["S4b"][1], "value": 1e3 / float(np.mean(tb)), "unit": "frames/s",
+                                    "ms_per_step": float(np.mean(tb)),
+                                    "mpixel_per_s": sb.width * sb.height * 1e3 / float(np.mean(tb)) / 1e6}}
+            sr.close(); db.free()
         if world == 1 and not args.no_cpu_baseline:
             run, desc = oracle_frame_sampler(scene, budget_s=10.0)
             t = float(np.mean([run() for _ in range(2)]))
@@ -365,6 +385,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary S4b reading")
     ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep the area-based strip partition")
     ap.add_argument("--pipeline", action="store_true",
                     help="N > 1: send the strip chunk by chunk while rendering the next chunk (measured slower on S5: "

@@ -42,8 +42,9 @@ def partition_rows(scene, n_ranks, tile_rows=256):
 
 def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenting_extra_ms=0.0):
     """Feedback partition: given the strips of the last frame and the time each rank spent on its strip,
-    assume cost is uniform inside a strip, and cut the canvas again so that every rank gets the same
-    estimated time (the presenting rank is charged `presenting_extra_ms` for receiving the others)."""
+    assume cost is uniform inside a strip and cut the canvas again (contiguous tile rows, one strip per
+    rank, in rank order) so that the largest estimated time is as small as possible; the presenting rank
+    is charged `presenting_extra_ms` for receiving the others.  Exact by dynamic programming."""
     n_rows = (height + tile_rows - 1) // tile_rows
     cost = np.zeros(n_rows)
     for (y0, y1), t in zip(rows, times_ms):
@@ -51,19 +52,24 @@ def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenti
         if b > a:
             cost[a:b] = max(t, 1e-3) / (b - a)
     n = len(rows)
-    total = cost.sum() + presenting_extra_ms
-    target = total / n
-    bounds = [0]
-    acc = 0.0
-    for k in range(n - 1):
-        want = target - (presenting_extra_ms if k == presenting else 0.0)
-        i = bounds[-1]
-        got = 0.0
-        while i < n_rows - (n - 1 - k) and (got + cost[i] * 0.5 < want or i == bounds[-1]):
-            got += cost[i]
-            i += 1
-        bounds.append(i)
-    bounds.append(n_rows)
+    if n_rows < n:
+        return list(rows)
+    pre = np.concatenate([[0.0], np.cumsum(cost)])
+    INF = float("inf")
+    best = [[INF] * (n_rows + 1) for _ in range(n + 1)]
+    cut = [[0] * (n_rows + 1) for _ in range(n + 1)]
+    best[0][0] = 0.0
+    for k in range(1, n + 1):
+        extra = presenting_extra_ms if (k - 1) == presenting else 0.0
+        for j in range(k, n_rows - (n - k) + 1):
+            for i in range(k - 1, j):
+                v = max(best[k - 1][i], pre[j] - pre[i] + extra)
+                if v < best[k][j]:
+                    best[k][j], cut[k][j] = v, i
+    bounds = [n_rows]
+    for k in range(n, 0, -1):
+        bounds.append(cut[k][bounds[-1]])
+    bounds = bounds[::-1]
     return [(bounds[k] * tile_rows, min(bounds[k + 1] * tile_rows, height)) for k in range(n)]
 
 
