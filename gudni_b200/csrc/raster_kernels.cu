@@ -122,9 +122,6 @@ __global__ void __launch_bounds__(kSweepWarpsPerCta * 32) raster_sweep_kernel(co
 // spill list with a grid stride, so the scratch footprint is fixed (slots x MAXTHRESHOLDS x 20 B)
 // regardless of how many threads spilled.
 __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, float4* thr, uint32_t* hdr, int slots) {
-    // spilled threads come from arbitrary tiles: the table is empty (count 0) and every layer
-    // takes the global-memory path
-    __shared__ TileTable sTable;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long n = P.counters[kCntSpilled];
     if (n > (unsigned long long)P.spillCapacity) n = (unsigned long long)P.spillCapacity;
@@ -140,7 +137,7 @@ __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, 
         q.cap = P.maxThresholds;
         // the first kernel does not count the thresholds of a thread it hands over
         int generated;
-        bool ok = rasterThread(P, sTable, 0u, g, q, P.tileThreadBase[tileIndex] + column, generated);
+        bool ok = rasterThread(P, g, q, P.tileThreadBase[tileIndex] + column, generated);
         if (generated > 0) atomicAdd(&P.counters[kCntThresholds], (unsigned long long)generated);
         if (!ok) atomicAdd(&P.counters[kCntOverflow], 1ull);
     }

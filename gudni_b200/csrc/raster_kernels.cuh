@@ -3,10 +3,6 @@
 #include "context.cuh"
 #include "raster_device.cuh"
 
-// Capacity of the on-chip (L1-resident local window) threshold queue of a column-thread.  Threads
-// that need more are replayed by the spill kernel against an HBM queue of spec.max_thresholds.
-constexpr int kChipQueueCapacity = 64;
-
 namespace gudni_launch {
 int rasterTiles(gudni_ctx* ctx, const gudni_dev::FrameParams& P, int tileBase, int nTiles);
 int rasterSpill(gudni_ctx* ctx, const gudni_dev::FrameParams& P);
