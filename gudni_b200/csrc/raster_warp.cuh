@@ -47,12 +47,15 @@ constexpr int kColorCacheLines = GUDNI_CACHE_LINES;  // direct mapped
 #define GUDNI_SECTIONS_PER_ROUND 6
 #endif
 constexpr int kSectionsPerRound = GUDNI_SECTIONS_PER_ROUND;   // section records a lane may hand to the resolver per round
-constexpr int kPendingCap = 48;        // stacks waiting to be composited
+#ifndef GUDNI_EVAL_PAIR
+#define GUDNI_EVAL_PAIR 1
+#endif
+constexpr int kPendingCap = GUDNI_EVAL_PAIR ? 96 : 48;   // stacks waiting to be composited
 #ifndef GUDNI_PENDING_FLUSH
-#define GUDNI_PENDING_FLUSH 27
+#define GUDNI_PENDING_FLUSH (GUDNI_EVAL_PAIR ? 48 : 27)
 #endif
 constexpr int kPendingFlush = GUDNI_PENDING_FLUSH;      // composite when this many are waiting (one per lane, most lanes busy)
-constexpr int kLogCap = 40;            // per-lane log entries between flushes
+constexpr int kLogCap = GUDNI_EVAL_PAIR ? 72 : 40;            // per-lane log entries between flushes
 constexpr uint8_t kLogInline = 0xFF;   // entry carries its colour
 constexpr uint8_t kLogPixelEnd = 0xFE; // marker: store the pixel
 
@@ -131,6 +134,64 @@ static __device__ __noinline__ float4 denseColorTame(const WarpScratch& W, uint6
         }
         lastId = id;
     }
+}
+
+// Two independent stacks per lane, composited in one branch-free loop so that the two dependent chains
+// (table lookup -> products -> reciprocal -> corrections) overlap: the walk is latency bound, not issue
+// bound.  Each chain performs exactly the operations of denseColorTame on its own stack; a finished
+// chain idles on selects until the other one is done.  The background is folded in as a last virtual
+// layer.
+struct TameChain {
+    uint32_t w3, w2, w1, w0;   // remaining stack bits
+    float4 base;
+    uint32_t lastId;
+    bool done;
+    __device__ __forceinline__ void init(uint64_t hi, uint64_t lo, bool valid) {
+        w3 = (uint32_t)(hi >> 32); w2 = (uint32_t)hi; w1 = (uint32_t)(lo >> 32); w0 = (uint32_t)lo;
+        base = make_float4(0.f, 0.f, 0.f, 0.f);
+        lastId = 0xFFFFFFFFu;
+        done = !valid;
+    }
+    __device__ __forceinline__ void step(const WarpScratch& W, float4 bgPremul) {
+        const bool h3 = w3 != 0u, h2 = w2 != 0u, h1 = w1 != 0u, h0 = w0 != 0u;
+        const bool none = !(h3 || h2 || h1 || h0);
+        const uint32_t word = h3 ? w3 : h2 ? w2 : h1 ? w1 : w0;
+        const int wordBase = h3 ? 96 : h2 ? 64 : h1 ? 32 : 0;
+        const int b = 31 - __clz((int)(word | 1u));   // word == 0 only when none
+        const uint32_t mask = none ? 0u : (1u << b);
+        w3 ^= h3 ? mask : 0u;
+        w2 ^= (!h3 && h2) ? mask : 0u;
+        w1 ^= (!h3 && !h2 && h1) ? mask : 0u;
+        w0 ^= (!h3 && !h2 && !h1) ? mask : 0u;
+        const int bit = none ? 0 : wordBase + b;
+        const uint32_t meta = none ? kMetaSet | 0x3FFFFFFEu : W.meta[bit];
+        const float4 pm = none ? bgPremul : W.premul[bit];
+        const uint32_t id = meta & kMetaIdMask;
+        const bool blend = !done && (id != lastId) && (meta & kMetaSet);
+        // composite (K.cl:878-887), computed unconditionally, kept only if this layer is blended
+        const float oneMinus = 1.0f - base.w;
+        const float alphaOut = base.w + pm.w * oneMinus;
+        float4 c;
+        div3<false>((base.x * base.w) + (pm.x * oneMinus), (base.y * base.w) + (pm.y * oneMinus),
+                    (base.z * base.w) + (pm.z * oneMinus), alphaOut > 0.0f ? alphaOut : 1.0f, c.x, c.y, c.z);
+        c.w = alphaOut;
+        if (!(alphaOut > 0.0f)) c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (blend) base = c;
+        if (!done) lastId = id;
+        done = done || none || (blend && base.w == 1.0f);
+    }
+};
+static __device__ __noinline__ void denseColorTamePair(const WarpScratch& W, ulonglong2 keyA, ulonglong2 keyB, bool validB,
+                                                       float4 bgPremul, float4& outA, float4& outB) {
+    TameChain a, b;
+    a.init(keyA.y, keyA.x, true);
+    b.init(keyB.y, keyB.x, validB);
+    while (!(a.done && b.done)) {
+        a.step(W, bgPremul);
+        b.step(W, bgPremul);
+    }
+    outA = a.base;
+    outB = b.base;
 }
 
 __device__ __forceinline__ uint32_t stackHash(uint64_t hi, uint64_t lo) {
@@ -265,15 +326,37 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
         // ---- flush: composite the pending stacks, replay the logs ----------------------------------
         const bool logFull = logLen > kLogCap - (kSectionsPerRound + 2);
         if (pendingCount >= kPendingFlush || !anyAlive || __any_sync(full, logFull)) {
-            for (int p0 = 0; p0 < pendingCount; p0 += 32) {
-                const int p = p0 + lane;
-                if (p < pendingCount) {
-                    const ulonglong2 key = W.pendKey[p];
-                    const float4 c = tame ? denseColorTame(W, key.y, key.x, bgPremul) : denseColor(P, W, key.y, key.x, bgPremul, 0, 0);
-                    W.pendColor[p] = c;
-                    // un-pin: the line that references this entry (if it got one) now holds the colour
-                    const uint32_t line = stackHash(key.y, key.x);
-                    if (W.cacheColor[line].w == -(float)(1 + p)) W.cacheColor[line] = make_float4(c.x, c.y, c.z, 1.f);
+            if (GUDNI_EVAL_PAIR && tame) {
+                for (int p0 = 0; p0 < pendingCount; p0 += 64) {
+                    const int pa = p0 + lane, pb = p0 + 32 + lane;
+                    if (pa < pendingCount) {
+                        const bool validB = pb < pendingCount;
+                        const ulonglong2 keyA = W.pendKey[pa];
+                        const ulonglong2 keyB = validB ? W.pendKey[pb] : make_ulonglong2(0ull, 0ull);
+                        float4 ca, cb;
+                        denseColorTamePair(W, keyA, keyB, validB, bgPremul, ca, cb);
+                        W.pendColor[pa] = ca;
+                        // un-pin: the line that references this entry (if it got one) now holds the colour
+                        const uint32_t lineA = stackHash(keyA.y, keyA.x);
+                        if (W.cacheColor[lineA].w == -(float)(1 + pa)) W.cacheColor[lineA] = make_float4(ca.x, ca.y, ca.z, 1.f);
+                        if (validB) {
+                            W.pendColor[pb] = cb;
+                            const uint32_t lineB = stackHash(keyB.y, keyB.x);
+                            if (W.cacheColor[lineB].w == -(float)(1 + pb)) W.cacheColor[lineB] = make_float4(cb.x, cb.y, cb.z, 1.f);
+                        }
+                    }
+                }
+            } else {
+                for (int p0 = 0; p0 < pendingCount; p0 += 32) {
+                    const int p = p0 + lane;
+                    if (p < pendingCount) {
+                        const ulonglong2 key = W.pendKey[p];
+                        const float4 c = tame ? denseColorTame(W, key.y, key.x, bgPremul) : denseColor(P, W, key.y, key.x, bgPremul, 0, 0);
+                        W.pendColor[p] = c;
+                        // un-pin: the line that references this entry (if it got one) now holds the colour
+                        const uint32_t line = stackHash(key.y, key.x);
+                        if (W.cacheColor[line].w == -(float)(1 + p)) W.cacheColor[line] = make_float4(c.x, c.y, c.z, 1.f);
+                    }
                 }
             }
             __syncwarp();
