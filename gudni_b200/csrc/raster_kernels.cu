@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kSweepWarpsPerCta * 32) raster_sweep_kernel(co
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch& W = scratch[warp];
-    QueueCold<kQueueCap - kQueueHot> cold;
+    QueueCold<kQueueCap> cold;
     LaneLog log;
     LaneQueue q;
     q.cold = &cold;

@@ -32,9 +32,9 @@ constexpr int kWarpTableCap = 128;
 #endif
 constexpr int kQueueCap = GUDNI_QUEUE_CAP;          // thresholds per column-thread before the HBM replay takes over
 #ifndef GUDNI_QUEUE_HOT
-#define GUDNI_QUEUE_HOT 12
+#define GUDNI_QUEUE_HOT 8
 #endif
-constexpr int kQueueHot = GUDNI_QUEUE_HOT;           // of which in shared memory (sweep kernel)
+constexpr int kQueueHot = GUDNI_QUEUE_HOT;           // head window in shared memory (sweep kernel; power of two)
 #ifndef GUDNI_GEN_QUEUE_HOT
 #define GUDNI_GEN_QUEUE_HOT 8
 #endif
@@ -50,7 +50,10 @@ constexpr int kSectionsPerRound = GUDNI_SECTIONS_PER_ROUND;   // section records
 #ifndef GUDNI_EVAL_PAIR
 #define GUDNI_EVAL_PAIR 1
 #endif
-constexpr int kPendingCap = GUDNI_EVAL_PAIR ? 96 : 48;   // stacks waiting to be composited
+#ifndef GUDNI_PENDING_CAP
+#define GUDNI_PENDING_CAP (GUDNI_EVAL_PAIR ? 80 : 48)
+#endif
+constexpr int kPendingCap = GUDNI_PENDING_CAP;   // stacks waiting to be composited
 #ifndef GUDNI_PENDING_FLUSH
 #define GUDNI_PENDING_FLUSH (GUDNI_EVAL_PAIR ? 48 : 27)
 #endif
@@ -64,7 +67,7 @@ struct WarpScratch {
     uint32_t meta[kWarpTableCap];                    //   512 B
     ulonglong2 cacheKey[kColorCacheLines];           // 2,048 B  colour cache: stack (lo, hi)
     float4 cacheColor[kColorCacheLines];             // 2,048 B  colour; w < 0 marks an empty line
-    uint32_t cacheClaim[kColorCacheLines];           //   512 B
+    uint8_t cacheClaim[kColorCacheLines];            //   128 B
     ulonglong2 pendKey[kPendingCap];                 // 1,024 B  stacks to composite
     float4 pendColor[kPendingCap];                   // 1,024 B  ... and their colours once composited
     ulonglong2 recKey[32 * kSectionsPerRound];       // 2,048 B  records of the round: stack, then colour / reference
@@ -72,7 +75,7 @@ struct WarpScratch {
     float4 qThr[kQueueHot * 32];                     // 4,096 B  hot part of the 32 threshold queues
     uint32_t qHdr[kQueueHot * 32];                   // 1,024 B
 };
-typedef WarpQueue<kQueueCap, kQueueHot> LaneQueue;
+typedef HeadQueue<kQueueCap, kQueueHot> LaneQueue;
 
 // per-lane log of sections whose colour was not known when they were swept
 struct LaneLog {
@@ -301,12 +304,7 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
     st.alive = false;
     q.init();
     if (rec.count != kRecInactive) {
-        q.start = kQueueCap - (int)rec.count;
-        q.len = (int)rec.count;
-        for (int i = 0; i < (int)rec.count; i++) {
-            const float4 t = P.thrStore[rec.offset + i];
-            q.set(i, P.hdrStore[rec.offset + i], Thr{t.x, t.y, t.z, t.w});
-        }
+        q.attach(P.thrStore, P.hdrStore, rec.offset, (int)rec.count);
         st.init(floatHeight);
     }
     __syncwarp();
@@ -471,9 +469,9 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                 }
                 if (__any_sync(full, miss)) {
                     // new stacks: one claimant per line appends it to the pending list and pins the line
-                    if (miss) W.cacheClaim[line] = (uint32_t)lane;
+                    if (miss) W.cacheClaim[line] = (uint8_t)lane;
                     __syncwarp();
-                    const bool winner = miss && W.cacheClaim[line] == (uint32_t)lane;
+                    const bool winner = miss && W.cacheClaim[line] == (uint8_t)lane;
                     const unsigned winners = __ballot_sync(full, winner);
                     const int idx = pendingCount + __popc(winners & ((1u << lane) - 1u));
                     if (winner) {
