@@ -59,6 +59,8 @@ constexpr int kPendingCap = GUDNI_PENDING_CAP;   // stacks waiting to be composi
 #endif
 constexpr int kPendingFlush = GUDNI_PENDING_FLUSH;      // composite when this many are waiting (one per lane, most lanes busy)
 constexpr int kLogCap = GUDNI_EVAL_PAIR ? 72 : 40;            // per-lane log entries between flushes
+constexpr int kLinelessSlots = 64;
+constexpr uint8_t kLinelessNone = 0xFF;
 constexpr uint8_t kLogInline = 0xFF;   // entry carries its colour
 constexpr uint8_t kLogPixelEnd = 0xFE; // marker: store the pixel
 
@@ -68,6 +70,7 @@ struct WarpScratch {
     ulonglong2 cacheKey[kColorCacheLines];           // 2,048 B  colour cache: stack (lo, hi)
     float4 cacheColor[kColorCacheLines];             // 2,048 B  colour; w < 0 marks an empty line
     uint8_t cacheClaim[kColorCacheLines];            //   128 B
+    uint8_t lineless[kLinelessSlots];                //    64 B  pending stacks without a cache line: hash -> pending index
     ulonglong2 pendKey[kPendingCap];                 // 1,024 B  stacks to composite
     float4 pendColor[kPendingCap];                   // 1,024 B  ... and their colours once composited
     ulonglong2 recKey[32 * kSectionsPerRound];       // 2,048 B  records of the round: stack, then colour / reference
@@ -197,12 +200,22 @@ static __device__ __noinline__ void denseColorTamePair(const WarpScratch& W, ulo
     outB = b.base;
 }
 
-__device__ __forceinline__ uint32_t stackHash(uint64_t hi, uint64_t lo) {
+// two candidate lines per stack (never the same line)
+__device__ __forceinline__ void stackLines(uint64_t hi, uint64_t lo, uint32_t& line1, uint32_t& line2) {
     uint32_t t = (uint32_t)lo ^ ((uint32_t)(lo >> 32) * 0x85EBCA6Bu) ^ ((uint32_t)hi * 0xC2B2AE35u) ^
                  ((uint32_t)(hi >> 32) * 0x27D4EB2Fu);
     t ^= t >> 15;
     t *= 0x2C1B3C6Du;
-    return (t >> 20) & (uint32_t)(kColorCacheLines - 1);
+    line1 = (t >> 20) & (uint32_t)(kColorCacheLines - 1);
+    line2 = line1 ^ (((t >> 9) & (uint32_t)(kColorCacheLines - 1)) | 1u);
+}
+
+__device__ __forceinline__ uint32_t linelessHash(uint64_t hi, uint64_t lo) {
+    uint32_t t = ((uint32_t)lo * 0x9E3779B1u) ^ ((uint32_t)(lo >> 32) * 0x7FEB352Du) ^ ((uint32_t)hi * 0x846CA68Bu) ^
+                 ((uint32_t)(hi >> 32) * 0x58F38DEDu);
+    t ^= t >> 16;
+    t *= 0x2C1B3C6Du;
+    return (t >> 24) & (uint32_t)(kLinelessSlots - 1);
 }
 
 // ---- generate kernel body -----------------------------------------------------------------------
@@ -293,6 +306,7 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
     const bool cacheable = !__any_sync(full, anyPicture);
     const bool tame = cacheable && !__any_sync(full, anyWild) && substanceIsTame(P.background);
     for (int i = lane; i < kColorCacheLines; i += 32) W.cacheColor[i] = make_float4(0.f, 0.f, 0.f, -1000.f);
+    if (lane < kLinelessSlots / 4) reinterpret_cast<uint32_t*>(W.lineless)[lane] = 0xFFFFFFFFu;
     // ---- the thread's sorted queue and initial stack, from the generate kernel ------------------------
     const ThreadRec rec = P.threadRecs[(size_t)unit * 32 + lane];
     ShapeStack stack;
@@ -335,12 +349,16 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                         denseColorTamePair(W, keyA, keyB, validB, bgPremul, ca, cb);
                         W.pendColor[pa] = ca;
                         // un-pin: the line that references this entry (if it got one) now holds the colour
-                        const uint32_t lineA = stackHash(keyA.y, keyA.x);
+                        uint32_t lineA, lineA2;
+                        stackLines(keyA.y, keyA.x, lineA, lineA2);
                         if (W.cacheColor[lineA].w == -(float)(1 + pa)) W.cacheColor[lineA] = make_float4(ca.x, ca.y, ca.z, 1.f);
+                        else if (W.cacheColor[lineA2].w == -(float)(1 + pa)) W.cacheColor[lineA2] = make_float4(ca.x, ca.y, ca.z, 1.f);
                         if (validB) {
                             W.pendColor[pb] = cb;
-                            const uint32_t lineB = stackHash(keyB.y, keyB.x);
+                            uint32_t lineB, lineB2;
+                            stackLines(keyB.y, keyB.x, lineB, lineB2);
                             if (W.cacheColor[lineB].w == -(float)(1 + pb)) W.cacheColor[lineB] = make_float4(cb.x, cb.y, cb.z, 1.f);
+                            else if (W.cacheColor[lineB2].w == -(float)(1 + pb)) W.cacheColor[lineB2] = make_float4(cb.x, cb.y, cb.z, 1.f);
                         }
                     }
                 }
@@ -352,8 +370,10 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                         const float4 c = tame ? denseColorTame(W, key.y, key.x, bgPremul) : denseColor(P, W, key.y, key.x, bgPremul, 0, 0);
                         W.pendColor[p] = c;
                         // un-pin: the line that references this entry (if it got one) now holds the colour
-                        const uint32_t line = stackHash(key.y, key.x);
+                        uint32_t line, line2;
+                        stackLines(key.y, key.x, line, line2);
                         if (W.cacheColor[line].w == -(float)(1 + p)) W.cacheColor[line] = make_float4(c.x, c.y, c.z, 1.f);
+                        else if (W.cacheColor[line2].w == -(float)(1 + p)) W.cacheColor[line2] = make_float4(c.x, c.y, c.z, 1.f);
                     }
                 }
             }
@@ -382,6 +402,7 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
 #endif
             logLen = 0;
             pendingCount = 0;
+            if (lane < kLinelessSlots / 4) reinterpret_cast<uint32_t*>(W.lineless)[lane] = 0xFFFFFFFFu;
             __syncwarp();
             if (!anyAlive) break;
         }
@@ -456,16 +477,35 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                 float4 out = make_float4(0.f, 0.f, 0.f, 0.f);   // w = 1: colour; w = -(1 + pending index): reference
                 if (valid) {
                     key = W.recKey[slot];
-                    line = stackHash(key.y, key.x);
+                    uint32_t line2;
+                    stackLines(key.y, key.x, line, line2);
                     const float4 c = W.cacheColor[line];
                     const ulonglong2 k = W.cacheKey[line];
-                    const bool same = k.x == key.x && k.y == key.y;
-                    if (same && c.w > -999.f) out = c;                       // ready colour or pending reference
 #ifdef GUDNI_STATS
-                    nRec++; if (same && c.w > 0.f) nReady++; else if (same && c.w > -999.f) nPendHit++;
+                    nRec++;
 #endif
-                    else if (c.w < 0.f && c.w > -999.f) slow = true;         // line pinned by another pending stack
-                    else miss = true;
+                    if (k.x == key.x && k.y == key.y && c.w > -999.f) {
+                        out = c;                                             // ready colour or pending reference
+                    } else {
+                        const float4 c2 = W.cacheColor[line2];
+                        const ulonglong2 k2 = W.cacheKey[line2];
+                        if (k2.x == key.x && k2.y == key.y && c2.w > -999.f) {
+                            out = c2;
+                        } else {
+                            // a new stack takes an empty line if it has one, else evicts a ready colour; a line
+                            // that waits for its colour (pinned until the flush) cannot be taken
+                            const bool empty1 = c.w <= -999.f, empty2 = c2.w <= -999.f;
+                            const bool pinned1 = c.w < 0.f && !empty1, pinned2 = c2.w < 0.f && !empty2;
+                            if (empty1) miss = true;
+                            else if (empty2) { miss = true; line = line2; }
+                            else if (!pinned1) miss = true;
+                            else if (!pinned2) { miss = true; line = line2; }
+                            else slow = true;
+                        }
+                    }
+#ifdef GUDNI_STATS
+                    if (out.w > 0.f) nReady++; else if (out.w < 0.f) nPendHit++;
+#endif
                 }
                 if (__any_sync(full, miss)) {
                     // new stacks: one claimant per line appends it to the pending list and pins the line
@@ -497,34 +537,33 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                         else slow = true;
                     }
                 }
-                // leftovers, one after the other: already pending? else append without a cache line
+                // leftovers: a stack that could not get a cache line is found again through a small hash of
+                // the line-less pending entries; what is not there is appended, one distinct stack at a time
+                // (a collision in that hash at worst appends a stack twice, which only costs its compositing)
+                uint32_t slotL = 0;
+                if (slow) {
+                    slotL = linelessHash(key.y, key.x);
+                    const uint8_t at = W.lineless[slotL];
+                    if (at != kLinelessNone) {
+                        const ulonglong2 k = W.pendKey[at];
+                        if (k.x == key.x && k.y == key.y) { out.w = -(float)(1 + (int)at); slow = false; }
+                    }
+                }
 #ifdef GUDNI_STATS
                 if (slow) nSlow++;
 #endif
                 unsigned todo = __ballot_sync(full, slow);
                 while (todo) {
                     const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
                     const unsigned long long kx = __shfl_sync(full, key.x, src), ky = __shfl_sync(full, key.y, src);
-                    bool match = false;
-                    int matchIdx = 0;
-                    for (int p = lane; p < pendingCount; p += 32) {
-                        const ulonglong2 k = W.pendKey[p];
-                        if (k.x == kx && k.y == ky) { match = true; matchIdx = p; }
-                    }
-                    const unsigned found = __ballot_sync(full, match);
-                    int idx;
-                    if (found) {
-                        idx = __shfl_sync(full, matchIdx, __ffs(found) - 1);
-                    } else if (pendingCount < kPendingCap) {
-                        idx = pendingCount;
-                        if (lane == 0) W.pendKey[idx] = make_ulonglong2(kx, ky);
+                    const bool mine = slow && key.x == kx && key.y == ky;
+                    todo &= ~__ballot_sync(full, mine);
+                    const int idx = pendingCount < kPendingCap ? pendingCount : -1;
+                    if (idx >= 0) {
+                        if (lane == src) { W.pendKey[idx] = key; W.lineless[slotL] = (uint8_t)idx; }
                         pendingCount++;
-                        __syncwarp();
-                    } else {
-                        idx = -1;
                     }
-                    if (lane == src) {
+                    if (mine) {
                         if (idx >= 0) out.w = -(float)(1 + idx);
                         else { const float4 c = denseColor(P, W, ky, kx, bgPremul, 0, 0); out = make_float4(c.x, c.y, c.z, 1.f); }
                     }
