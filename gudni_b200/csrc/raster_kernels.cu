@@ -47,16 +47,14 @@ __global__ void __launch_bounds__(kGenWarpsPerCta * 32, GUDNI_GEN_MIN_CTAS) rast
     q.thrHot = scratch[warp].qThr + lane;
     q.hdrHot = scratch[warp].qHdr + lane;
     const int warpShift = P.computeDepth - 5;                    // warps per tile = threadsPerTile / 32
-    const unsigned totalUnits = (unsigned)nTiles << warpShift;
     const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
-    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkGenerate);
+    unsigned int* cursors = reinterpret_cast<unsigned int*>(P.counters + 32);
+    StreamCursor cursor;
+    cursor.init(P.numStreams);
     for (;;) {
-        unsigned unit = 0;
-        if (lane == 0) unit = atomicAdd(workCounter, 1u);
-        unit = __shfl_sync(full, unit, 0);
-        if (unit >= totalUnits) break;
-        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> warpShift)];
-        const unsigned warpInTile = unit & ((1u << warpShift) - 1u);
+        unsigned int tileSlot, warpInTile;
+        if (!streamNext(cursor, cursors, P.numStreams, nTiles, warpShift, tileSlot, warpInTile)) break;
+        const int tileIndex = (int)P.tileOrder[tileBase + (int)tileSlot];
         const int column = (int)(warpInTile << 5) + lane;
         const unsigned recUnit = ((unsigned)tileIndex << warpShift) + warpInTile;   // thread records are indexed by tile, not by hand-out order
         const gudni_tile tile = P.tiles[tileIndex];
@@ -233,8 +231,9 @@ int selftestDiv3(gudni_ctx* ctx, unsigned long long n, unsigned long long seed, 
     return GUDNI_OK;
 }
 
-int rasterTiles(gudni_ctx* ctx, const FrameParams& P, int tileBase, int nTiles) {
+int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTiles) {
     if (nTiles <= 0) return GUDNI_OK;
+    FrameParams P = frame;
     static int genCtasPerSm = 0, sweepCtasPerSm = 0, numSms = 0;
     const size_t sweepSmem = kSweepWarpsPerCta * sizeof(WarpScratch);
     if (!genCtasPerSm) {
@@ -247,8 +246,9 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& P, int tileBase, int nTiles) 
         if (genCtasPerSm < 1) genCtasPerSm = 1;
         if (sweepCtasPerSm < 1) sweepCtasPerSm = 1;
     }
+    P.numStreams = std::max(1, std::min(std::min(numSms, gudni_dev::kMaxSms), nTiles));
     // work counters of the two kernels (the threshold store cursor runs on across the jobs of a frame)
-    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkGenerate, 0, 8, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 32, 0, gudni_dev::kMaxSms * sizeof(unsigned int), ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkSweep, 0, 8, ctx->stream));
     const long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
     const int genGrid = (int)std::min<long long>((long long)genCtasPerSm * numSms, (units + kGenWarpsPerCta - 1) / kGenWarpsPerCta);

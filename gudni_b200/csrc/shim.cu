@@ -159,7 +159,7 @@ int gudni_b200_init(int device, const gudni_spec* want, gudni_spec* got, gudni_c
                           &ctx->evDownloadDone, &ctx->evFirstKernel};
     for (cudaEvent_t* e : evs)
         if (cudaEventCreate(e) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
-    if (devEnsure(ctx, ctx->counters, 256) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
+    if (devEnsure(ctx, ctx->counters, gudni_dev::kCountersBytes) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
     ctx->spillCapacity = kSpillListCapacity;
     if (devEnsure(ctx, ctx->spillList, (size_t)kSpillListCapacity * 8) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
     ctx->spillSlots = kSpillSlots;
