@@ -79,7 +79,10 @@ __global__ void __launch_bounds__(kGenWarpsPerCta * 32, GUDNI_GEN_MIN_CTAS) rast
     }
 }
 
-__global__ void __launch_bounds__(kSweepWarpsPerCta * 32) raster_sweep_kernel(const FrameParams P, int tileBase, int nTiles) {
+#ifndef GUDNI_SWEEP_MIN_CTAS
+#define GUDNI_SWEEP_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(kSweepWarpsPerCta * 32, GUDNI_SWEEP_MIN_CTAS) raster_sweep_kernel(const FrameParams P, int tileBase, int nTiles) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smemRaw);
     const unsigned full = 0xffffffffu;
