@@ -62,7 +62,9 @@ constexpr int kLogCap = GUDNI_EVAL_PAIR ? 72 : 40;            // per-lane log en
 constexpr int kLinelessSlots = 64;
 constexpr uint8_t kLinelessNone = 0xFF;
 constexpr uint8_t kLogInline = 0xFF;   // entry carries its colour
-constexpr uint8_t kLogPixelEnd = 0xFE; // marker: store the pixel
+constexpr uint8_t kLogPixelEnd = 0x7F; // markers kLogPixelEnd + n, n = 1 .. kMaxBlankRun: store the pixel n times
+constexpr int kMaxBlankRun = 0xFE - 0x7F;
+static_assert(kPendingCap <= 0x7F, "log tags below kLogPixelEnd are pending indices");
 
 struct WarpScratch {
     float4 premul[kWarpTableCap];                    // 2,048 B  tile substance table
@@ -333,6 +335,7 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
     int logLen = 0;        // entries in this lane's log
     int wrow = 0;          // pixels of the slab stored so far (rows complete in order)
     int pendingCount = 0;  // warp-uniform
+    int blankRun = 1;      // pixels the band being swept stands for
     for (;;) {
         const bool anyAlive = __any_sync(full, st.alive);
         // ---- flush: composite the pending stacks, replay the logs ----------------------------------
@@ -380,10 +383,12 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
             __syncwarp();
             for (int j = 0; j < logLen; j++) {   // replay in section order (K.cl:1904)
                 const uint8_t tag = log.tag[j];
-                if (tag == kLogPixelEnd) {
-                    outp[(size_t)wrow * P.width] = pixelWord(st.accR, st.accG, st.accB, st.accArea);
+                if (tag > kLogPixelEnd && tag != kLogInline) {
+                    const uint32_t word = pixelWord(st.accR, st.accG, st.accB, st.accArea);
+                    const int rep = (int)tag - (int)kLogPixelEnd;
+                    for (int r = 0; r < rep; r++) outp[(size_t)(wrow + r) * P.width] = word;
                     st.accR = st.accG = st.accB = st.accArea = 0.f;
-                    wrow++;
+                    wrow += rep;
                     continue;
                 }
                 float4 r = log.rec[j];
@@ -410,20 +415,43 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
         if (lane == 0) nRounds++;
 #endif
         // ---- (A) band boundary: close the pixel, open the next band ---------------------------------
+        // A pixel no threshold touches is one band with one section of area exactly 1: its accumulators are
+        // colour * 1 and 1.  When the next threshold starts m or more whole pixels further down, the next m
+        // pixels of the column are that same pixel (same stack, same arithmetic), so the band is swept once
+        // and the pixel stored m times (`blankRun`, set when the band is opened).  Picture substances
+        // depend on the row, so their tiles do not take the shortcut.
         if (st.alive && st.ex == 1.0f) {
             if (st.ey >= st.pixelY) {   // calculatePixel's loop condition failed: the pixel is complete
                 if (logLen == 0) {      // everything of this pixel is accumulated
-                    outp[(size_t)wrow * P.width] = pixelWord(st.accR, st.accG, st.accB, st.accArea);
+                    const uint32_t word = pixelWord(st.accR, st.accG, st.accB, st.accArea);
+                    outp[(size_t)wrow * P.width] = word;
                     st.accR = st.accG = st.accB = st.accArea = 0.f;
                     wrow++;
+                    if (blankRun > 1) {
+                        for (int r = 1; r < blankRun; r++) outp[(size_t)(wrow + r - 1) * P.width] = word;
+                        wrow += blankRun - 1;
+                    }
                 } else {
-                    log.tag[logLen++] = kLogPixelEnd;
+                    log.tag[logLen++] = (uint8_t)(kLogPixelEnd + blankRun);
                 }
                 nextPixel(st, floatHeight);
+                if (blankRun > 1) {     // ... and the blankRun - 1 pixels after it
+                    const float skipped = (float)(blankRun - 1);
+                    st.sy += skipped;
+                    st.ey = st.sy;
+                    st.pixelY += skipped;
+                    st.row += blankRun - 1;
+                    st.alive = st.pixelY <= floatHeight;
+                }
             }
             if (st.alive) {
                 sweepVertical(q, stack, st, floatHeight);
                 if (q.failed()) { spilled = true; st.alive = false; }
+                blankRun = 1;
+                if (cacheable && st.sy == st.pixelY - 1.0f) {
+                    const float limit = fminf(st.gapTop, floatHeight);
+                    if (limit >= st.pixelY + 1.0f) blankRun = min((int)(limit - st.pixelY) + 1, kMaxBlankRun);
+                }
             }
         }
         // ---- (B) up to kSectionsPerRound sections of the band ---------------------------------------
