@@ -88,10 +88,8 @@ __global__ void __launch_bounds__(kSweepWarpsPerCta * 32, GUDNI_SWEEP_MIN_CTAS) 
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch& W = scratch[warp];
-    QueueCold<kQueueCap> cold;
     LaneLog log;
     LaneQueue q;
-    q.cold = &cold;
     q.thrHot = W.qThr + lane;
     q.hdrHot = W.qHdr + lane;
     const int warpShift = P.computeDepth - 5;

@@ -59,6 +59,10 @@ constexpr int kPendingCap = GUDNI_PENDING_CAP;   // stacks waiting to be composi
 #endif
 constexpr int kPendingFlush = GUDNI_PENDING_FLUSH;      // composite when this many are waiting (one per lane, most lanes busy)
 constexpr int kLogCap = GUDNI_EVAL_PAIR ? 72 : 40;            // per-lane log entries between flushes
+#ifndef GUDNI_STORE_SLACK
+#define GUDNI_STORE_SLACK 8
+#endif
+constexpr int kStoreSlack = GUDNI_STORE_SLACK;   // free store entries in front of every queue (see HeadQueue)
 constexpr int kLinelessSlots = 64;
 constexpr uint8_t kLinelessNone = 0xFF;
 constexpr uint8_t kLogInline = 0xFF;   // entry carries its colour
@@ -254,7 +258,10 @@ __device__ __forceinline__ int generateWarp(const FrameParams& P, GenQueue& q, c
             count = q.len;
         }
     }
-    int incl = count;
+    // each non-empty queue gets kStoreSlack free entries in front of it: the sweep keeps the part of the
+    // queue that is not in shared memory in this slice, and slicing makes a queue grow at its head
+    int reserve = count > 0 ? count + kStoreSlack : 0;
+    int incl = reserve;
     for (int d = 1; d < 32; d <<= 1) {
         const int t = __shfl_up_sync(full, incl, d);
         if (lane >= d) incl += t;
@@ -267,7 +274,7 @@ __device__ __forceinline__ int generateWarp(const FrameParams& P, GenQueue& q, c
         spilled = spilled || g.active;
         count = 0;
     }
-    const unsigned int offset = (unsigned int)(base + (unsigned long long)(incl - count));
+    const unsigned int offset = (unsigned int)(base + (unsigned long long)(incl - reserve + kStoreSlack));
     for (int i = 0; i < count; i++) {
         const Thr t = q.getT(i);
         P.thrStore[offset + i] = make_float4(t.top, t.bottom, t.left, t.right);
@@ -320,7 +327,7 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
     st.alive = false;
     q.init();
     if (rec.count != kRecInactive) {
-        q.attach(P.thrStore, P.hdrStore, rec.offset, (int)rec.count);
+        q.attach(P.thrStore, P.hdrStore, rec.offset, (int)rec.count, kStoreSlack);
         st.init(floatHeight);
     }
     __syncwarp();
@@ -381,8 +388,16 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                 }
             }
             __syncwarp();
-            for (int j = 0; j < logLen; j++) {   // replay in section order (K.cl:1904)
-                const uint8_t tag = log.tag[j];
+            // replay in section order (K.cl:1904).  The log is in local memory (L2 latency): the next entry is
+            // fetched, tag and record together, before the current one is applied.
+            uint8_t tagNext = log.tag[0];
+            float4 recNext = log.rec[0];
+            for (int j = 0; j < logLen; j++) {
+                const uint8_t tag = tagNext;
+                float4 r = recNext;
+                const int jn = min(j + 1, kLogCap - 1);
+                tagNext = log.tag[jn];
+                recNext = log.rec[jn];
                 if (tag > kLogPixelEnd && tag != kLogInline) {
                     const uint32_t word = pixelWord(st.accR, st.accG, st.accB, st.accArea);
                     const int rep = (int)tag - (int)kLogPixelEnd;
@@ -391,7 +406,6 @@ __device__ __forceinline__ int sweepWarp(const FrameParams& P, WarpScratch& W, L
                     wrow += rep;
                     continue;
                 }
-                float4 r = log.rec[j];
                 if (tag != kLogInline) {
                     const float4 c = W.pendColor[tag];
                     r.x = c.x; r.y = c.y; r.z = c.z;
