@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kGenWarpsPerCta * 32, GUDNI_GEN_MIN_CTAS) rast
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     QueueCold<kQueueCap - kGenQueueHot> cold;
     GenQueue q;
+    q.limit = min(kQueueCap, P.maxThresholds);
     q.cold = &cold;
     q.thrHot = scratch[warp].qThr + lane;
     q.hdrHot = scratch[warp].qHdr + lane;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kSweepWarpsPerCta * 32, GUDNI_SWEEP_MIN_CTAS) 
     WarpScratch& W = scratch[warp];
     LaneLog log;
     LaneQueue q;
+    q.limit = min(kQueueCap, P.maxThresholds);
     q.thrHot = W.qThr + lane;
     q.hdrHot = W.qHdr + lane;
     const int warpShift = P.computeDepth - 5;

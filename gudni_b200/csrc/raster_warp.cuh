@@ -28,7 +28,7 @@ namespace gudni_dev {
 
 constexpr int kWarpTableCap = 128;
 #ifndef GUDNI_QUEUE_CAP
-#define GUDNI_QUEUE_CAP 64
+#define GUDNI_QUEUE_CAP 256
 #endif
 constexpr int kQueueCap = GUDNI_QUEUE_CAP;          // thresholds per column-thread before the HBM replay takes over
 #ifndef GUDNI_QUEUE_HOT

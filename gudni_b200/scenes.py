@@ -317,16 +317,24 @@ def s2(width=1920, height=1080, lines=30, em=30.0, seed=0x5EED0002):
     return b.freeze()
 
 
-def thin_rectangles(n, width=64, height=None, spacing=1.0, thickness=0.5, skew=0.3, background=(1.0, 1.0, 1.0, 1.0)):
+def thin_rectangles(n, width=64, height=None, spacing=1.0, thickness=0.5, skew=0.3, background=(1.0, 1.0, 1.0, 1.0),
+                    one_shape=False):
     """maxThresholdTest / maxShapeTest flavour (benchmarks/GudniTests.hs:100-127): a stack of wide, thin,
-    slightly skewed translucent rectangles — hundreds of thresholds per pixel column.  ONE substance, so
-    tiles are not forced to split by the shape cap... they are: each rectangle is a shape; use a small
-    canvas so tiles bottom out at 8 px and keep everything."""
+    slightly skewed translucent rectangles — hundreds of thresholds per pixel column.  Each rectangle is
+    a shape with its own substance, so more than MAXSHAPE of them make the tiles split; `one_shape`
+    puts all the outlines into a single shape instead (one substance, tiles stay whole, every column of
+    a tall tile crosses 2 n thresholds)."""
     height = int(n * spacing + 8) if height is None else height
-    b = SceneBuilder(width, height, background, name=f"thinRects-{n}")
+    b = SceneBuilder(width, height, background, name=f"thinRects-{n}" + ("-one" if one_shape else ""))
+    outlines = []
     for i in range(n):
-        s = b.solid(0.9 * ((i * 37) % 11) / 10.0, 0.9 * ((i * 53) % 7) / 6.0, 0.5, 0.4)
         y = np.float32(2.0 + i * spacing)
         pts = [(-1.0, float(y)), (width + 1.0, float(y + skew)), (width + 1.0, float(y + skew + thickness)), (-1.0, float(y + thickness))]
-        b.shape(s, [_straight_outline(pts)])
+        if one_shape:
+            outlines.append(_straight_outline(pts))
+        else:
+            s = b.solid(0.9 * ((i * 37) % 11) / 10.0, 0.9 * ((i * 53) % 7) / 6.0, 0.5, 0.4)
+            b.shape(s, [_straight_outline(pts)])
+    if one_shape:
+        b.shape(b.solid(0.1, 0.3, 0.6, 0.6), outlines)
     return b.freeze()

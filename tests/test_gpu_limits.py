@@ -15,11 +15,22 @@ from parity import level1_parity, level2_parity
 pytestmark = pytest.mark.gpu
 
 
-def test_long_queues_take_the_replay_path(rasterizer):
-    # tall tile columns crossing ~2 thresholds per rectangle: well over the 64-entry on-chip queue
+def test_long_queues_stay_on_chip(rasterizer):
+    # ~120 thresholds per column-thread: far beyond the 8-entry shared-memory window, inside the 256-entry
+    # on-chip capacity (the queue tail lives in the threshold store)
     scene = scenes.thin_rectangles(60, width=64, spacing=3.0, thickness=1.3)
     img, stats, ref = level1_parity(rasterizer, scene)
     assert max(int(c.max()) for c in ref.n_thresholds) > 64
+    assert stats.n_spilled_threads == 0 and stats.n_overflow_threads == 0
+    level2_parity(rasterizer, scene, ref=ref)
+
+
+def test_very_long_queues_take_the_replay_path(rasterizer):
+    # one shape of 150 thin rectangles on a 256-wide tile: every column-thread is 256 rows tall and crosses
+    # ~300 thresholds, over the 256-entry on-chip capacity, under MAXTHRESHOLDS
+    scene = scenes.thin_rectangles(150, width=256, height=256, spacing=1.5, thickness=0.7, one_shape=True)
+    img, stats, ref = level1_parity(rasterizer, scene)
+    assert max(int(c.max()) for c in ref.n_thresholds) > 256
     assert stats.n_spilled_threads > 0 and stats.n_overflow_threads == 0
     level2_parity(rasterizer, scene, ref=ref)
 
@@ -36,8 +47,8 @@ def test_threshold_overflow_is_reported_not_corrupting():
     spec = RasterSpec(max_thresholds=16)
     r = setup_rasterizer(spec=spec)
     try:
-        # ~100 thresholds per column-thread: past the 64-entry on-chip queue, so the threads are replayed
-        # against HBM queues of max_thresholds = 16 entries, which they overflow
+        # ~100 thresholds per column-thread: the on-chip capacity is capped by max_thresholds = 16, so the
+        # threads are replayed against HBM queues of 16 entries, which they overflow (and report)
         scene = scenes.thin_rectangles(100, width=32, spacing=3.0, thickness=1.3)
         img, stats = r.raster_scene(0, scene)
         assert stats.n_spilled_threads > 0
