@@ -70,7 +70,8 @@ int ensureFrameBuffer(gudni_ctx* ctx) {
 int ensureHandover(gudni_ctx* ctx, int64_t totalTiles) {
     const size_t threads = (size_t)totalTiles * (size_t)ctx->spec.threads_per_tile;
     const size_t pixels = (size_t)ctx->width * (size_t)(ctx->rowEnd - ctx->rowBegin);
-    const size_t entries = std::max({threads * 16, pixels / 4, (size_t)(ctx->storeDemand + ctx->storeDemand / 4), (size_t)1 << 20});
+    // first guess: 16 thresholds + the 8 slack entries (kStoreSlack) per column-thread; afterwards the last frame's demand
+    const size_t entries = std::max({threads * 24, pixels / 4, (size_t)(ctx->storeDemand + ctx->storeDemand / 4), (size_t)1 << 20});
     GUDNI_TRY(devEnsure(ctx, ctx->thrStore, entries * 16));
     GUDNI_TRY(devEnsure(ctx, ctx->hdrStore, entries * 4));
     ctx->storeCap = std::min(ctx->thrStore.cap / 16, ctx->hdrStore.cap / 4);
