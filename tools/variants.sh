@@ -1,6 +1,6 @@
 #!/bin/bash
-# usage: tools_variants.sh name1 "flags1" name2 "flags2" ...   builds variants into gpurun_in/
-mkdir -p gpurun_in; rm -f gpurun_in/lib_*.so
+# usage: tools/variants.sh name1 "flags1" name2 "flags2" ...   builds variants into gpurun_in/
+cd "$(dirname "$0")/.." && mkdir -p gpurun_in; rm -f gpurun_in/lib_*.so
 while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
   python -c "
