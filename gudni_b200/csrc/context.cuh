@@ -44,6 +44,7 @@ struct gudni_ctx {
     DevBuf shapes, tiles, tileThreadBase;
     int64_t nShapes = 0, nTiles = 0, nColumns = 0;
     int64_t rasteredTiles = 0;   // tiles already covered by a raster launch this frame
+    int64_t rasteredShapes = 0;  // ... and the shape records of those tiles' jobs
 
     // output
     DevBuf frame;

@@ -107,6 +107,7 @@ int beginFrameCommon(gudni_ctx* ctx, const float bg[4], int width, int height, i
     ctx->rowEnd = height;
     ctx->nShapes = ctx->nTiles = ctx->nColumns = 0;
     ctx->rasteredTiles = 0;
+    ctx->rasteredShapes = 0;
     ctx->firstKernelRecorded = false;
     ctx->binUsed = false;
     ctx->inFrame = true;
@@ -257,6 +258,23 @@ int gudni_b200_frame_strip(gudni_ctx* ctx, int row_begin, int row_end) {
     return GUDNI_OK;
 }
 
+// rasterize the tiles of the jobs queued since the last launch (level 1)
+constexpr int64_t kLaunchTiles = 2048;
+static int launchPendingJobs(gudni_ctx* ctx) {
+    const int64_t pending = ctx->nTiles - ctx->rasteredTiles;
+    if (pending <= 0) return GUDNI_OK;
+    GUDNI_TRY(ensureHandover(ctx, ctx->nTiles));
+    markFirstKernel(ctx);
+    GUDNI_TRY(devEnsure(ctx, ctx->strandBounds, ctx->geometryBytes / 2 + 16));
+    GUDNI_TRY(gudni_launch::strandBounds(ctx, ctx->geometryPtr, ctx->shapes.as<gudni_shape>() + ctx->rasteredShapes,
+                                         (int)sizeof(gudni_shape), (int)(ctx->nShapes - ctx->rasteredShapes),
+                                         ctx->strandBounds.as<float2>()));
+    GUDNI_TRY(gudni_launch::rasterTiles(ctx, makeParams(ctx), (int)ctx->rasteredTiles, (int)pending));
+    ctx->rasteredTiles = ctx->nTiles;
+    ctx->rasteredShapes = ctx->nShapes;
+    return GUDNI_OK;
+}
+
 // raster + generateCall, OpenCL/CallKernels.hs:88-206
 int gudni_b200_raster_job(gudni_ctx* ctx, const gudni_shape* shapes, int n_shapes, const gudni_tile* tiles, int n_tiles,
                           int columns_allocated, int job_index) {
@@ -296,17 +314,13 @@ int gudni_b200_raster_job(gudni_ctx* ctx, const gudni_shape* shapes, int n_shape
                                         cudaMemcpyHostToDevice, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tileThreadBase.as<int32_t>() + ctx->nTiles, base.data(), (size_t)n_tiles * 4,
                                         cudaMemcpyHostToDevice, ctx->stream));
-    const int tileBase = (int)ctx->nTiles;
     ctx->nShapes += n_shapes;
     ctx->nTiles += n_tiles;
     ctx->nColumns += columns_allocated;
-    GUDNI_TRY(ensureHandover(ctx, ctx->nTiles));
-    markFirstKernel(ctx);
-    GUDNI_TRY(devEnsure(ctx, ctx->strandBounds, ctx->geometryBytes / 2 + 16));
-    GUDNI_TRY(gudni_launch::strandBounds(ctx, ctx->geometryPtr, ctx->shapes.as<gudni_shape>() + (ctx->nShapes - n_shapes),
-                                         (int)sizeof(gudni_shape), n_shapes, ctx->strandBounds.as<float2>()));
-    GUDNI_TRY(gudni_launch::rasterTiles(ctx, makeParams(ctx), tileBase, n_tiles));
-    ctx->rasteredTiles = ctx->nTiles;
+    // The reference launches its kernels once per job (<= G tiles); a job that small leaves most of a
+    // B200 idle, so jobs are collected and rasterized together, kLaunchTiles at a time or at frame_end
+    // (nothing reads the bitmap before frame_end).
+    if (ctx->nTiles - ctx->rasteredTiles >= kLaunchTiles) GUDNI_TRY(launchPendingJobs(ctx));
     return GUDNI_OK;
 }
 
@@ -352,6 +366,7 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     GUDNI_TRY(ensureFrameBuffer(ctx));
     if (ctx->nTiles) {
+        GUDNI_TRY(launchPendingJobs(ctx));
         GUDNI_TRY(gudni_launch::rasterSpill(ctx, makeParams(ctx)));
     } else {
         markFirstKernel(ctx);
