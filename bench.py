@@ -216,18 +216,21 @@ def run_native(args, rank, world, local_rank):
     for i in range(args.warmup):
         render(i)
     if world > 1 and args.gather == "nccl" and not args.no_rebalance:
-        # feedback partition (contiguous tile-row strips stay): two rounds of "measure every rank's strip,
+        # feedback partition (contiguous tile-row strips stay): a few rounds of "measure every rank's strip,
         # cut the canvas again so the estimated times are equal"; the presenting rank is charged for the
         # gather it receives
         from gudni_b200.strips import rebalance_rows
-        for it in range(2):
+        for it in range(args.rebalance_rounds):
             st = getattr(strips, "last_stats", None)
             mine = torch.tensor([st.ms_raster + st.ms_bin if st is not None else 0.0], dtype=torch.float64, device="cuda")
             allr = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(allr, mine)
             times = [float(x.item()) for x in allr]
-            gather_ms = 4.0 * scene.width * scene.height * (world - 1) / world / 700e9 * 1e3
-            new_rows = rebalance_rows(strips.rows, times, scene.height, r.spec.max_tile_size, 0, gather_ms)
+            # the presenting rank posts its receives first (StripRenderer.render), so the strips queue on its
+            # inbound links in the order their ranks finish: charge each strip the transfer of everything
+            # from its first row down, at what the link delivered in earlier runs
+            row_ms = 4.0 * scene.width * r.spec.max_tile_size / args.gather_gbs / 1e9 * 1e3
+            new_rows = rebalance_rows(strips.rows, times, scene.height, r.spec.max_tile_size, 0, 0.0, row_ms)
             if new_rows == strips.rows:
                 break
             strips.close(); dscene.free()
@@ -387,6 +390,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary S4b reading")
     ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep the area-based strip partition")
+    ap.add_argument("--rebalance-rounds", type=int, default=4, help="N > 1: feedback rounds of the strip rebalancer")
+    ap.add_argument("--gather-gbs", type=float, default=800.0,
+                    help="N > 1: inbound GB/s of the presenting rank assumed by the strip rebalancer (measured ~780 on NVLink 5)")
     ap.add_argument("--pipeline", action="store_true",
                     help="N > 1: send the strip chunk by chunk while rendering the next chunk (measured slower on S5: "
                          "a 256-row chunk cannot fill a B200, see DESIGN.md §5)")

@@ -40,11 +40,19 @@ def partition_rows(scene, n_ranks, tile_rows=256):
     return [(bounds[k] * tile_rows, min(bounds[k + 1] * tile_rows, scene.height)) for k in range(n_ranks)]
 
 
-def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenting_extra_ms=0.0):
+def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenting_extra_ms=0.0, row_transfer_ms=0.0):
     """Feedback partition: given the strips of the last frame and the time each rank spent on its strip,
     assume cost is uniform inside a strip and cut the canvas again (contiguous tile rows, one strip per
-    rank, in rank order) so that the largest estimated time is as small as possible; the presenting rank
-    is charged `presenting_extra_ms` for receiving the others.  Exact by dynamic programming."""
+    rank, in rank order) so that the frame completes as early as possible.  Exact by dynamic programming.
+
+    Cost model.  The presenting rank posts its receives before it starts its own strip, so a strip starts
+    to arrive as soon as its rank has finished it, and the strips share the presenting rank's inbound
+    links: with `row_transfer_ms` per tile row, a strip that starts at tile row i cannot be complete
+    before its own rank is done plus the time to move everything from row i down (the ranks below it
+    finish later and queue behind it).  Minimising the latest of those makes the ranks finish staggered,
+    top to bottom, each one just as the link frees up, instead of all together with the whole gather
+    still to go.  `presenting_extra_ms` is a flat charge on the presenting rank (receives posted after
+    its own work, the older scheme)."""
     n_rows = (height + tile_rows - 1) // tile_rows
     cost = np.zeros(n_rows)
     for (y0, y1), t in zip(rows, times_ms):
@@ -60,10 +68,15 @@ def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenti
     cut = [[0] * (n_rows + 1) for _ in range(n + 1)]
     best[0][0] = 0.0
     for k in range(1, n + 1):
-        extra = presenting_extra_ms if (k - 1) == presenting else 0.0
+        is_presenting = (k - 1) == presenting
         for j in range(k, n_rows - (n - k) + 1):
             for i in range(k - 1, j):
-                v = max(best[k - 1][i], pre[j] - pre[i] + extra)
+                finish = pre[j] - pre[i]
+                if is_presenting:
+                    finish += presenting_extra_ms
+                else:
+                    finish += (n_rows - i) * row_transfer_ms if presenting == 0 else (j - i) * row_transfer_ms
+                v = max(best[k - 1][i], finish)
                 if v < best[k][j]:
                     best[k][j], cut[k][j] = v, i
     bounds = [n_rows]
@@ -174,8 +187,13 @@ class StripRenderer:
         r, torch = self.r, self.torch
         rows = self.my_rows
         active = rows[1] > rows[0]
+        early = None
         if self.rank == self.presenting:
             r.frame_target(self.canvas.data_ptr(), 0)
+            if self.world > 1 and self.mode == "nccl":
+                # receives first: a strip then flows in as soon as its rank is done with it, while this rank
+                # (and the slower ones) are still rasterizing
+                early = self.post_receives(self.dist, self.rank, self.rows, self.canvas)
         elif self.mode == "p2p":
             r.frame_target(self._peer_canvas, 0)
         else:
@@ -193,8 +211,18 @@ class StripRenderer:
                 r.raster_entries(self.entries)
             _, self.last_stats = r.frame_end(want_image=False)
         if self.world > 1:
-            self._gather()
+            if early is not None:
+                for req in early:
+                    req.wait()
+            else:
+                self._gather()
         return self.canvas
+
+    @staticmethod
+    def post_receives(dist, rank, rows, canvas):
+        """One irecv per remote strip, straight into the canvas rows; returns the requests."""
+        ops = [dist.P2POp(dist.irecv, canvas[y0:y1], k) for k, (y0, y1) in enumerate(rows) if k != rank and y1 > y0]
+        return dist.batch_isend_irecv(ops) if ops else []
 
     def _gather(self):
         dist, torch = self.dist, self.torch

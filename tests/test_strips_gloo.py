@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, result_path):
+def _worker(rank, world, port, result_path, early):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -32,9 +32,19 @@ def _worker(rank, world, port, result_path):
     image = oracle.render(local, taps=False, threads=2).image
     strip = torch.from_numpy(image[y0:y1].view(np.int32).copy())
     canvas = torch.zeros((scene.height, scene.width), dtype=torch.int32) if rank == 0 else None
-    if rank == 0:
-        canvas[y0:y1] = strip
-    StripRenderer.gather_strips(dist, rank, 0, rows, strip, canvas)
+    if early:
+        # the presenting rank posts its receives before it has produced its own strip (StripRenderer.render)
+        reqs = StripRenderer.post_receives(dist, rank, rows, canvas) if rank == 0 else None
+        if rank == 0:
+            canvas[y0:y1] = strip
+            for q in reqs:
+                q.wait()
+        else:
+            StripRenderer.gather_strips(dist, rank, 0, rows, strip, canvas)
+    else:
+        if rank == 0:
+            canvas[y0:y1] = strip
+        StripRenderer.gather_strips(dist, rank, 0, rows, strip, canvas)
     if rank == 0:
         full = oracle.render(scene, taps=False, threads=2).image
         np.save(result_path, np.array([int(np.array_equal(canvas.numpy().view(np.uint32), full))]))
@@ -42,11 +52,31 @@ def _worker(rank, world, port, result_path):
     dist.destroy_process_group()
 
 
-def test_two_rank_strip_gather(tmp_path):
-    port = 29600 + (os.getpid() % 300)
+@pytest.mark.parametrize("early", [False, True], ids=["gather-after", "receives-posted-first"])
+def test_two_rank_strip_gather(tmp_path, early):
+    port = 29600 + (os.getpid() % 300) + (7 if early else 0)
     result = str(tmp_path / "ok.npy")
-    mp.spawn(_worker, args=(2, port, result), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, result, early), nprocs=2, join=True)
     assert np.load(result)[0] == 1
+
+
+def test_rebalance_rows_staggers_the_finishing_times():
+    sys.path.insert(0, ROOT)
+    from gudni_b200.strips import rebalance_rows
+    height, tile = 64 * 256, 256
+    even = [(k * 8 * tile, (k + 1) * 8 * tile) for k in range(8)]
+    times = [4.0] * 8                      # uniform cost: 0.5 ms per tile row
+    flat = rebalance_rows(even, times, height, tile)
+    assert flat == even                    # nothing to gain without a transfer cost
+    stag = rebalance_rows(even, times, height, tile, presenting=0, row_transfer_ms=0.02)
+    assert stag[0][0] == 0 and stag[-1][1] == height
+    assert all(a[1] == b[0] for a, b in zip(stag, stag[1:]))
+    sizes = [(b - a) // tile for a, b in stag]
+    # lower strips finish later (their data queues behind the strips above), so they may be larger
+    assert sizes[1] <= sizes[-1] and sizes != [8] * 8
+    done = [0.5 * n + (64 - a // tile) * 0.02 * (k != 0) for k, ((a, b), n) in enumerate(zip(stag, sizes))]
+    done_even = [4.0 + (64 - 8 * k) * 0.02 * (k != 0) for k in range(8)]
+    assert max(done) < max(done_even)
 
 
 def test_partition_rows_is_contiguous_and_balanced():
