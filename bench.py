@@ -215,30 +215,63 @@ def run_native(args, rank, world, local_rank):
         barrier()
     for i in range(args.warmup):
         render(i)
+    gather_order = None
     if world > 1 and args.gather == "nccl" and not args.no_rebalance:
-        # feedback partition (contiguous tile-row strips stay): a few rounds of "measure every rank's strip,
-        # cut the canvas again so the estimated times are equal"; the presenting rank is charged for the
-        # gather it receives
+        # Feedback partition (contiguous tile-row strips stay): a few rounds of "measure every rank's strip, cut
+        # the canvas again", under each of the two gather orders, keeping the faster one:
+        #   early  the presenting rank posts its receives before its own strip; strips queue on its inbound
+        #          links in the order their ranks finish, so each strip is charged the transfer of everything
+        #          from its first row down (ranks finish staggered); the receive kernel holds some SMs meanwhile
+        #   late   receives after the presenting rank's strip: nothing arrives before it is done, so it is charged
+        #          the transfer of all the other strips too
         from gudni_b200.strips import rebalance_rows
-        for it in range(args.rebalance_rounds):
-            st = getattr(strips, "last_stats", None)
-            mine = torch.tensor([st.ms_raster + st.ms_bin if st is not None else 0.0], dtype=torch.float64, device="cuda")
-            allr = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(allr, mine)
-            times = [float(x.item()) for x in allr]
-            # the presenting rank posts its receives first (StripRenderer.render), so the strips queue on its
-            # inbound links in the order their ranks finish: charge each strip the transfer of everything
-            # from its first row down, at what the link delivered in earlier runs
-            row_ms = 4.0 * scene.width * r.spec.max_tile_size / args.gather_gbs / 1e9 * 1e3
-            new_rows = rebalance_rows(strips.rows, times, scene.height, r.spec.max_tile_size, 0, 0.0, row_ms)
-            if new_rows == strips.rows:
-                break
+        row_ms = 4.0 * scene.width * r.spec.max_tile_size / args.gather_gbs / 1e9 * 1e3
+        start_rows = list(strips.rows)
+
+        def frame_ms(n=3):
+            t = []
+            for i in range(n):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); render(i); e1.record(stream)
+                barrier()
+                t.append(e0.elapsed_time(e1))
+            m = torch.tensor([float(np.mean(t))], dtype=torch.float64, device="cuda")
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            return float(m.item())
+
+        def rebuild(rows, early):
+            nonlocal strips, dscene, render
             strips.close(); dscene.free()
-            strips = StripRenderer(r, scene, rank, world, dist, mode=args.gather, rows=new_rows)
+            strips = StripRenderer(r, scene, rank, world, dist, mode=args.gather, rows=rows, early_receives=early)
             dscene = DeviceScene(r, scene, entries=strips.entries)
             render = lambda f: strips.render(f, dscene)
             for i in range(2):
                 render(i)
+
+        tried = {}
+        orders = ["early", "late"] if args.gather_order == "auto" else [args.gather_order]
+        for order in orders:
+            rebuild(start_rows, order == "early")
+            for it in range(args.rebalance_rounds):
+                st = getattr(strips, "last_stats", None)
+                mine = torch.tensor([st.ms_raster + st.ms_bin if st is not None else 0.0], dtype=torch.float64, device="cuda")
+                allr = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(allr, mine)
+                times = [float(x.item()) for x in allr]
+                if order == "early":
+                    new_rows = rebalance_rows(strips.rows, times, scene.height, r.spec.max_tile_size, 0, 0.0, row_ms)
+                else:
+                    new_rows = rebalance_rows(strips.rows, times, scene.height, r.spec.max_tile_size, 0, 0.0, row_ms,
+                                              late_receives=True)
+                if new_rows == strips.rows:
+                    break
+                rebuild(new_rows, order == "early")
+            tried[order] = (frame_ms(), list(strips.rows))
+        gather_order = min(tried, key=lambda k: tried[k][0])
+        if len(tried) > 1 or strips.rows != tried[gather_order][1]:
+            rebuild(tried[gather_order][1], gather_order == "early")
+        gather_order = {"order": gather_order, "warmup_ms": {k: round(v[0], 3) for k, v in tried.items()}}
     launches0 = r.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -328,7 +361,8 @@ def run_native(args, rank, world, local_rank):
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": "1 GPU, whole frame" if world == 1 else
                        f"{world} tile-row strips, gather={args.gather}" + (f", pipelined in chunks of {args.chunk_rows} rows" if pipelined else ""),
-                       "strips": strips.rows if world > 1 else None},
+                       "strips": strips.rows if world > 1 else None,
+                       "gather_order": gather_order},
             "mpixel_per_s": scene.width * scene.height * value / 1e6,
             "clocks": clocks,
             "e2e": {"value": 1.0 / float(t_e2e.item()), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
@@ -390,6 +424,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary S4b reading")
     ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep the area-based strip partition")
+    ap.add_argument("--gather-order", choices=("auto", "early", "late"), default="auto",
+                    help="N > 1: post the presenting rank's receives before (early) or after (late) its own strip; auto measures both")
     ap.add_argument("--rebalance-rounds", type=int, default=4, help="N > 1: feedback rounds of the strip rebalancer")
     ap.add_argument("--gather-gbs", type=float, default=800.0,
                     help="N > 1: inbound GB/s of the presenting rank assumed by the strip rebalancer (measured ~780 on NVLink 5)")

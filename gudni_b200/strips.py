@@ -40,7 +40,8 @@ def partition_rows(scene, n_ranks, tile_rows=256):
     return [(bounds[k] * tile_rows, min(bounds[k + 1] * tile_rows, scene.height)) for k in range(n_ranks)]
 
 
-def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenting_extra_ms=0.0, row_transfer_ms=0.0):
+def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenting_extra_ms=0.0, row_transfer_ms=0.0,
+                   late_receives=False):
     """Feedback partition: given the strips of the last frame and the time each rank spent on its strip,
     assume cost is uniform inside a strip and cut the canvas again (contiguous tile rows, one strip per
     rank, in rank order) so that the frame completes as early as possible.  Exact by dynamic programming.
@@ -51,8 +52,9 @@ def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenti
     before its own rank is done plus the time to move everything from row i down (the ranks below it
     finish later and queue behind it).  Minimising the latest of those makes the ranks finish staggered,
     top to bottom, each one just as the link frees up, instead of all together with the whole gather
-    still to go.  `presenting_extra_ms` is a flat charge on the presenting rank (receives posted after
-    its own work, the older scheme)."""
+    still to go.  With `late_receives` the presenting rank posts its receives after its own strip:
+    nothing can arrive before it is done, so it is charged the transfer of every other strip as well.
+    `presenting_extra_ms` is a flat charge on the presenting rank."""
     n_rows = (height + tile_rows - 1) // tile_rows
     cost = np.zeros(n_rows)
     for (y0, y1), t in zip(rows, times_ms):
@@ -74,6 +76,8 @@ def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenti
                 finish = pre[j] - pre[i]
                 if is_presenting:
                     finish += presenting_extra_ms
+                    if late_receives:
+                        finish += (n_rows - (j - i)) * row_transfer_ms
                 else:
                     finish += (n_rows - i) * row_transfer_ms if presenting == 0 else (j - i) * row_transfer_ms
                 v = max(best[k - 1][i], finish)
@@ -89,11 +93,15 @@ def rebalance_rows(rows, times_ms, height, tile_rows=256, presenting=0, presenti
 class StripRenderer:
     """Per-rank driver.  `dist` is torch.distributed (already initialised) or None for one GPU."""
 
-    def __init__(self, rasterizer, scene, rank=0, world=1, dist=None, mode="nccl", presenting_rank=0, rows=None):
+    def __init__(self, rasterizer, scene, rank=0, world=1, dist=None, mode="nccl", presenting_rank=0, rows=None,
+                 early_receives=True):
         import torch
         self.torch = torch
         self.r, self.scene, self.rank, self.world, self.dist = rasterizer, scene, rank, world, dist
         self.mode = mode if world > 1 else "local"
+        # receives posted before the presenting rank's own strip (the strips then arrive while it rasterizes, at
+        # the price of the receive kernel holding some SMs meanwhile) or after it
+        self.early_receives = early_receives
         self.presenting = presenting_rank
         self.rows = rows if rows is not None else partition_rows(scene, world, rasterizer.spec.max_tile_size)
         while len(self.rows) < world:
@@ -190,7 +198,7 @@ class StripRenderer:
         early = None
         if self.rank == self.presenting:
             r.frame_target(self.canvas.data_ptr(), 0)
-            if self.world > 1 and self.mode == "nccl":
+            if self.world > 1 and self.mode == "nccl" and self.early_receives:
                 # receives first: a strip then flows in as soon as its rank is done with it, while this rank
                 # (and the slower ones) are still rasterizing
                 early = self.post_receives(self.dist, self.rank, self.rows, self.canvas)
