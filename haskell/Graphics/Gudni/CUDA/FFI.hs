@@ -47,3 +47,16 @@ foreign import ccall safe "gudni_b200_last_error"
 
 foreign import ccall safe "gudni_b200_destroy"
   c_destroy :: Ptr GudniCtx -> IO ()
+
+-- | Optional: page-lock a long-lived caller buffer (a Pile's allocation, the HostBitmapTarget) so the
+-- per-frame copies run at full PCIe rate; unregister before freeing / after a Pile has grown.
+foreign import ccall safe "gudni_b200_host_register"
+  c_hostRegister :: Ptr GudniCtx -> Ptr () -> CSize -> IO CInt
+
+foreign import ccall safe "gudni_b200_host_unregister"
+  c_hostUnregister :: Ptr GudniCtx -> Ptr () -> IO CInt
+
+-- | Optional (multi-GPU hosts, one process per device): restrict the frame to whole root-tile rows
+-- [rowBegin, rowEnd) of the canvas; call between frame_begin and the raster calls.
+foreign import ccall safe "gudni_b200_frame_strip"
+  c_frameStrip :: Ptr GudniCtx -> CInt -> CInt -> IO CInt
