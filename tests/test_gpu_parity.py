@@ -5,7 +5,7 @@ import pytest
 from gudni_b200 import scenes
 from gudni_b200.formats import RasterSpec
 
-from parity import level1_parity
+from parity import level1_parity, level2_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -62,3 +62,12 @@ def test_picture_substances(rasterizer):
 
 def test_s2_paragraph_reduced(rasterizer):
     level1_parity(rasterizer, scenes.s2(960, 540, lines=14))
+
+
+def test_level1_jobs_are_collected_across_launches(rasterizer):
+    # 10 jobs / 2,325 tiles: the queued jobs are launched once 2,048 tiles are waiting and the rest at
+    # frame_end; thread counts, taps and pixels must not depend on where the launches fall
+    scene = scenes.fuzzy_circles(30000, 2048, 1024, 5, 50, 0x7117)
+    img, stats, ref = level1_parity(rasterizer, scene)
+    assert len(ref.jobs) >= 2 and stats.n_tiles > 2048
+    level2_parity(rasterizer, scene, ref=ref)

@@ -89,3 +89,16 @@ def test_partition_rows_is_contiguous_and_balanced():
         assert rows[0][0] == 0 and rows[-1][1] == scene.height
         assert all(a[1] == b[0] and a[0] % 256 == 0 for a, b in zip(rows, rows[1:]))
         assert len(rows) == min(n, 16)
+
+
+def test_rebalance_rows_late_receives_charges_the_presenting_rank():
+    sys.path.insert(0, ROOT)
+    from gudni_b200.strips import rebalance_rows
+    height, tile = 64 * 256, 256
+    halves = [(0, 32 * tile), (32 * tile, height)]
+    # two ranks, uniform cost, receives posted after the presenting rank's strip: both must finish together
+    # (the transfer follows whichever is later), so the halves stay
+    assert rebalance_rows(halves, [10.0, 10.0], height, tile, presenting=0, row_transfer_ms=0.02, late_receives=True) == halves
+    # early receives: the lower strip may finish later by less than its own transfer time
+    early = rebalance_rows(halves, [10.0, 10.0], height, tile, presenting=0, row_transfer_ms=0.02)
+    assert early[0][1] >= halves[0][1]
