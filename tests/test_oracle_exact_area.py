@@ -121,3 +121,51 @@ def test_two_translucent_polygons_composite_top_over_bottom(seed):
             expected[y, x] = (a_tb * over_tb + (a_t - a_tb) * over_t + (a_b - a_tb) * over_b +
                               (1.0 - a_t - a_b + a_tb) * bg)
     _check(got, expected)
+
+
+def _flatten(outline, steps=24):
+    """The outline's quadratic Beziers (anchor_i, control_i, anchor_i+1) as a fine polygon; the harness'
+    circle starts with a degenerate closing pair (a reference quirk), whose zero-length edges are dropped."""
+    pts = []
+    k = len(outline)
+    for i in range(k):
+        a, c, b = outline[i, :2].astype(np.float64), outline[i, 2:].astype(np.float64), outline[(i + 1) % k, :2].astype(np.float64)
+        for j in range(steps):
+            t = j / steps
+            q = tuple((1 - t) ** 2 * a + 2 * (1 - t) * t * c + t * t * b)
+            if not pts or abs(q[0] - pts[-1][0]) + abs(q[1] - pts[-1][1]) > 1e-4:
+                pts.append(q)
+    signed = sum(pts[i][0] * pts[(i + 1) % len(pts)][1] - pts[(i + 1) % len(pts)][0] * pts[i][1] for i in range(len(pts)))
+    return pts if signed > 0 else pts[::-1]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_curved_outline_coverage_within_the_flatness_tolerance(seed):
+    # strands, tree search and curve bisection: a circle of 16 quadratic arcs.  The reference bisects a curve
+    # until it is flat to 0.25 pixel (taxicab) and takes the chord, so edge pixels may be off by about a
+    # tenth; everything else must be exact.
+    from gudni_b200.scenes import _circle_outline
+    rng = np.random.default_rng(3000 + seed)
+    cx, cy = rng.uniform(0.3 * SIZE, 0.7 * SIZE, 2)
+    r = rng.uniform(3.0, 0.28 * SIZE)
+    outline = _circle_outline([("translate", float(cx), float(cy)), ("scale", float(r))])
+    poly = _flatten(outline)
+    col, bg = rng.uniform(0, 1, 3), rng.uniform(0, 1, 3)
+    b = SceneBuilder(SIZE, SIZE, (float(bg[0]), float(bg[1]), float(bg[2]), 1.0), name="exact-area-circle")
+    b.shape(b.solid(float(col[0]), float(col[1]), float(col[2]), 1.0), [outline])
+    img = oracle.render(b.freeze(), taps=False).image
+    got = np.stack([(img >> 16) & 0xFF, (img >> 8) & 0xFF, img & 0xFF], axis=-1).astype(np.float64) / 255.0
+    cover = np.zeros((SIZE, SIZE))
+    for y in range(SIZE):
+        for x in range(SIZE):
+            cover[y, x] = _area(_clip_to_convex(_pixel(float(x), float(y)), poly))
+    expected = cover[..., None] * col + (1.0 - cover[..., None]) * bg
+    err = np.abs(got - expected).max(axis=-1)
+    assert err.max() <= 0.15 and err.mean() <= 0.01
+    # pixels the edge does not come near (neither they nor their neighbours are cut): exact
+    whole = (cover < 1e-9) | (cover > 1.0 - 1e-9)
+    far = whole.copy()
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            far &= np.roll(np.roll(whole, dy, axis=0), dx, axis=1)
+    assert err[far].max() <= 1.5 / 255.0
