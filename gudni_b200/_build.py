@@ -70,3 +70,13 @@ def build_oracle(force=False, verbose=False):
     cmd = ["make", "-C", odir] + (["-B"] if force else [])
     subprocess.run(cmd, check=True, stdout=None if verbose else subprocess.DEVNULL)
     return os.path.join(odir, "libgudni_oracle.so")
+
+
+def build_reference(force=False, verbose=False):
+    """oracle/_ref/libgudni_ref.so: the reference's kernel file compiled for the host (checker and CPU
+    baseline only).  None when /root/reference is absent and nothing was prebuilt."""
+    import sys
+    if REPO not in sys.path:
+        sys.path.insert(0, REPO)
+    from oracle.refbuild import build_ref
+    return build_ref.build(force=force, verbose=verbose)

@@ -1,5 +1,5 @@
 // kernels_oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT.  See kernels_oracle.hpp for the header
-// comment (scope, "parity unpinned", who may call this).
+// comment (scope, how it is pinned to the reference, who may call this).
 //
 // Second half of the restatement of Kernels.cl ("K.cl"): curve traversal and threshold
 // generation, colour determination, the sweep, the three kernel bodies, and the host loop that

@@ -4,10 +4,17 @@
 // with no FMA contraction (build with -ffp-contract=off) and no fast-math.  Every function cites
 // the lines of /root/reference/src/Graphics/Gudni/OpenCL/Kernels.cl ("K.cl") it follows.
 //
-// PARITY UNPINNED: the reference has no automated tests, golden vectors or fixtures for this
-// path, and neither GHC nor an OpenCL runtime exists in this image, so the reference itself
-// cannot be run here.  The oracle is pinned instead by hand-derived
-// known-answer scenes (tests/test_oracle_known_answers.py) and structural invariants.
+// PINNED TO THE REFERENCE'S OWN KERNEL SOURCE.  The reference has no automated tests, golden vectors or
+// fixtures for this path, and its Haskell + OpenCL host cannot run in this image (no GHC, no OpenCL
+// runtime: SURVEY.md §4, §8(c)).  Its kernel file, however, compiles for the host: oracle/refbuild/
+// builds K.cl with g++ against an OpenCL-C compatibility header into oracle/_ref/libgudni_ref.so, and
+// tests/test_reference_pin.py requires this restatement to reproduce its per-thread threshold counts,
+// shape-bit counts and BGRA words exactly (every catalogue scene, seeded random scenes under three
+// RasterSpecs, pictures, glyphs, and S4b / S4 at full size: 14,114,195 thresholds, 8.3 M pixels, 0
+// differences).  tests/golden/ holds vectors that library produced.  What stays outside the pin:
+// -cl-fast-relaxed-math on a real OpenCL device (OpenCL/Setup.hs:129), not reproducible by definition.
+// Hand-derived known answers (tests/test_oracle_known_answers.py) and an independent exact-area renderer
+// (tests/test_oracle_exact_area.py) check that the algorithm itself computes what it claims.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // use this file.  Dead code of K.cl is deliberately not restated.

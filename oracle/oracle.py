@@ -1,7 +1,8 @@
 """ctypes driver of the CPU oracle (libgudni_oracle.so).  TEST INFRASTRUCTURE, NOT PRODUCT.
 
-PARITY UNPINNED: the reference holds no golden vectors for this path and cannot be run in this
-image (no GHC, no OpenCL runtime); see kernels_oracle.hpp.
+Pinned to the reference's own kernel file compiled for the host (oracle/_ref/libgudni_ref.so, built
+by oracle/refbuild/build_ref.py; `reference=True` below drives it): see kernels_oracle.hpp and
+tests/test_reference_pin.py.  The tile tree (Haskell) stays a restatement.
 
 `render(scene, spec)` plays the role of drawFrame's hot path (Application.hs:239-241):
 buildRasterJobs -> queueRasterJobs -> per job generate / sort / render.
@@ -17,6 +18,38 @@ from gudni_b200.formats import SHAPE_DTYPE, TILE_DTYPE, CSpec, RasterSpec, CANON
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libgudni_oracle.so")
 _lib = None
+
+
+_REF_PATH = os.path.join(_HERE, "_ref", "libgudni_ref.so")
+_ref_lib = None
+
+
+def build_reference(force=False):
+    """oracle/_ref/libgudni_ref.so — the reference's own Kernels.cl compiled for the host
+    (oracle/refbuild/build_ref.py).  Returns None when neither /root/reference nor a prebuilt
+    library is present."""
+    from oracle.refbuild import build_ref
+    return build_ref.build(force=force)
+
+
+def reference_lib():
+    """The compiled reference kernels, or None if they cannot be had (no reference tree and no
+    prebuilt library)."""
+    global _ref_lib
+    if _ref_lib is None:
+        path = build_reference()
+        if path is None:
+            return None
+        c = ctypes
+        L = ctypes.CDLL(path)
+        L.gudni_ref_threads.restype = c.c_int
+        L.gudni_ref_set_threads.argtypes = [c.c_int]
+        L.gudni_ref_raster_job.restype = c.c_int64
+        L.gudni_ref_raster_job.argtypes = [c.c_void_p] * 5 + [c.c_int, c.c_int, c.POINTER(CSpec), c.c_void_p,
+                                                              c.c_void_p, c.c_int, c.c_int, c.c_void_p,
+                                                              c.c_void_p, c.c_void_p, c.POINTER(c.c_int64)]
+        _ref_lib = L
+    return _ref_lib
 
 
 def build(force=False):
@@ -107,11 +140,21 @@ class RenderResult:
         self.jobs = jobs
 
 
-def raster_jobs(scene, jobs, spec: RasterSpec = CANONICAL_SPEC, taps=True, threads=None):
-    """queueRasterJobs (OpenCL/CallKernels.hs:218-242): every job through the three kernels."""
-    L = lib()
-    if threads:
-        L.gudni_oracle_set_threads(int(threads))
+def raster_jobs(scene, jobs, spec: RasterSpec = CANONICAL_SPEC, taps=True, threads=None, reference=False):
+    """queueRasterJobs (OpenCL/CallKernels.hs:218-242): every job through the three kernels —
+    the restated ones, or with `reference=True` the reference's own (oracle/_ref)."""
+    if reference:
+        L = reference_lib()
+        if L is None:
+            raise RuntimeError("oracle/_ref/libgudni_ref.so is not built and /root/reference is absent")
+        raster_job = L.gudni_ref_raster_job
+        if threads:
+            L.gudni_ref_set_threads(int(threads))
+    else:
+        L = lib()
+        raster_job = L.gudni_oracle_raster_job
+        if threads:
+            L.gudni_oracle_set_threads(int(threads))
     cs = spec.to_c()
     out = np.zeros((scene.height, scene.width), dtype=np.uint32)
     geometry = np.ascontiguousarray(scene.geometry)
@@ -128,7 +171,7 @@ def raster_jobs(scene, jobs, spec: RasterSpec = CANONICAL_SPEC, taps=True, threa
         tt = ctypes.c_int64(0)
         shapes = np.ascontiguousarray(job.shapes)
         tiles = np.ascontiguousarray(job.tiles)
-        overflow += L.gudni_oracle_raster_job(
+        overflow += raster_job(
             geometry.ctypes.data, substances.ctypes.data, pict.ctypes.data, uses.ctypes.data, bg.ctypes.data,
             scene.width, scene.height, ctypes.byref(cs), shapes.ctypes.data, tiles.ctypes.data, len(tiles),
             job.columns, out.ctypes.data, nt.ctypes.data if taps else None, sb.ctypes.data if taps else None,
@@ -139,8 +182,8 @@ def raster_jobs(scene, jobs, spec: RasterSpec = CANONICAL_SPEC, taps=True, threa
     return RenderResult(out, counts, bits, total, overflow, jobs)
 
 
-def render(scene, spec: RasterSpec = CANONICAL_SPEC, taps=True, threads=None):
-    return raster_jobs(scene, build_raster_jobs(scene, spec), spec, taps, threads)
+def render(scene, spec: RasterSpec = CANONICAL_SPEC, taps=True, threads=None, reference=False):
+    return raster_jobs(scene, build_raster_jobs(scene, spec), spec, taps, threads, reference)
 
 
 def host_threads():

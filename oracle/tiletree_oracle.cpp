@@ -6,7 +6,10 @@
 //       /root/reference/src/Graphics/Gudni/Raster/TileTree.hs:74-204
 //   accumulateRasterJobs / addTileToRasterJob   Raster/Job.hs:121-178
 //   buildRasterJobs (argument swap and job-list order)   OpenCL/CallKernels.hs:244-255
-// PARITY UNPINNED: the reference holds no fixtures for this path.
+// PARITY UNPINNED for this file: the reference holds no fixtures for the tile tree and, unlike the kernel
+// file (oracle/refbuild/), its Haskell source cannot be compiled in this image.  Checked by invariants
+// (every pixel in exactly one leaf, caps respected unless at the 8-pixel floor, shape order) and, end to
+// end, by images: a wrong tile assignment shows up as wrong pixels against oracle/_ref.
 #include <cstdint>
 #include <cstring>
 #include <memory>

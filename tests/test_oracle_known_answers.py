@@ -1,6 +1,7 @@
-"""Pins for the CPU oracle.  The reference has no tests or golden vectors for this path
-(SURVEY.md §4), so the oracle is pinned by scenes whose answer follows by hand from the reference's
-definitions: exact area coverage of axis-aligned rectangles, `composite` (Kernels.cl:878-887),
+"""Pins for the CPU oracle.  The reference has no tests or golden vectors of its own for this path
+(SURVEY.md §4); the oracle is pinned (1) by scenes whose answer follows by hand from the reference's
+definitions and (2) by golden vectors produced by the reference's own kernel source compiled for the
+host (tests/golden/, tests/test_reference_pin.py).  Hand-derived: exact area coverage of axis-aligned rectangles, `composite` (Kernels.cl:878-887),
 truncating BGRA conversion (:842-844), add/subtract semantics of determineColor (:1447-1513)."""
 import numpy as np
 import pytest
@@ -181,16 +182,25 @@ def test_picture_substance_texel_lookup():
         assert rgb(img, x, y)[:3] == want, (x, y, tx, ty)
 
 
-def test_oracle_matches_committed_golden_hashes():
-    """Regression pin of the oracle itself: image hashes generated by tests/golden/make_golden.py."""
-    import hashlib
+def test_oracle_matches_reference_golden_vectors():
+    """The restated oracle against vectors the REFERENCE'S OWN kernels produced
+    (tests/golden/reference_hashes.json, written by tests/golden/make_golden.py from
+    oracle/_ref/libgudni_ref.so = Kernels.cl compiled for the host): image, threshold total,
+    per-thread threshold counts and shape-bit counts, all bit-exact."""
     import json
     import os
-    path = os.path.join(os.path.dirname(__file__), "golden", "oracle_hashes.json")
+    from golden.make_golden import SCENES, digest, render
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_hashes.json")
     golden = json.load(open(path))
-    from golden.make_golden import SCENES
-    for name, make in SCENES.items():
-        r = oracle.render(make())
-        digest = hashlib.sha256(r.image.tobytes()).hexdigest()
-        assert digest == golden[name]["sha256"], name
-        assert r.total_thresholds == golden[name]["thresholds"], name
+    assert set(golden) == set(SCENES)
+    for name in SCENES:
+        assert digest(render(name, reference=False)) == golden[name], name
+
+
+def test_reference_golden_images_verbatim():
+    """The smallest golden scenes are stored as images too; the oracle reproduces them word for word."""
+    import os
+    from golden.make_golden import VERBATIM, render
+    stored = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_images.npz"))
+    for name in VERBATIM:
+        assert np.array_equal(render(name, reference=False).image, stored[name]), name
