@@ -376,7 +376,11 @@ static void calculatePixel(const FrameInputs& in, const TileState* tileS, Thresh
         pS->currentThreshold += 1;
     }
 }
-static inline uint32_t toByte(float v) { return (uint32_t)(uint8_t)(int32_t)v; }  // convert_uchar4: rtz, no saturation
+// convert_uchar4 (K.cl:843): round toward zero.  Out-of-range input (the signed section areas make a
+// channel slightly negative or above 255 on a few pixels per million) is undefined in OpenCL C without
+// _sat; this follows what the reference's kernels do on the one real OpenCL device they could be run on
+// (NVIDIA OpenCL 3.0 on the B200, profiles/r1_opencl_reference.json): clamp to [0,255], NaN -> 0.
+static inline uint32_t toByte(float v) { return v >= 255.0f ? 255u : (v > 0.0f ? (uint32_t)(int32_t)v : 0u); }
 static void writePixelGlobal(const TileState* tileS, float4 color, uint32_t* out, int y) {  // K.cl:842-844, 1853-1862
     uint32_t word = toByte(color.z * MAXCHANNELFLOAT) | (toByte(color.y * MAXCHANNELFLOAT) << 8) |
                     (toByte(color.x * MAXCHANNELFLOAT) << 16) | (toByte(1.0f * MAXCHANNELFLOAT) << 24);

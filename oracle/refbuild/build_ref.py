@@ -71,6 +71,43 @@ def rewritten_source():
     return text
 
 
+def opencl_source(max_thresholds=1024, strict=False):
+    """The text the reference hands to the OpenCL compiler (OpenCL/Setup.hs:132 addDefinesToSource):
+    Kernels.cl with its first 40 lines replaced by the #define block, MAXTHRESHOLDS a literal, and the
+    two places a current OpenCL compiler rejects patched (pos2's untyped parameters, :813, and an
+    address-space qualifier on a struct field, :420).  `strict` uses one of the padding lines
+    for `#pragma OPENCL FP_CONTRACT OFF`."""
+    with open(KERNELS_CL, "r", encoding="utf-8", errors="replace") as f:
+        lines = f.read().split("\n")
+    defines = [(k, str(int(max_thresholds)) if k == "MAXTHRESHOLDS" else v) for k, v in DEFINES]
+    head = ["#define %s %s" % d for d in defines]
+    if strict:
+        head.append("#pragma OPENCL FP_CONTRACT OFF")
+    head += ["// Padding line "] * (SOURCE_FILE_PADDING - len(head))
+    text = "\n".join(head + lines[SOURCE_FILE_PADDING:])
+    text, n = re.subn(r"inline int pos2 \(x, y, width\)", "inline int pos2 (int x, int y, int width)", text)
+    assert n == 1
+    # Kernels.cl:420 qualifies a struct FIELD with __private; NVIDIA's OpenCL 3.0 compiler rejects
+    # that ("field may not be qualified with an address space"), so the qualifier goes
+    text, n = re.subn(r"PMEM SHAPESTACK shapeStack\[SHAPESTACKSECTIONS\];", "SHAPESTACK shapeStack[SHAPESTACKSECTIONS];", text)
+    assert n == 1
+    return text
+
+
+def write_opencl_blob(path=None, max_thresholds=(1024, 256)):
+    """zlib-compressed program text for oracle/refbuild/ocl_run.py (the OpenCL runtime compiles from
+    source; there is no offline compiler in this image).  Lives under oracle/_ref/ (git-ignored)."""
+    import json
+    import zlib
+    path = path or os.path.join(OUT_DIR, "ocl_program.bin")
+    os.makedirs(OUT_DIR, exist_ok=True)
+    blob = json.dumps({str(m): {"reference": opencl_source(m, strict=False), "strict": opencl_source(m, strict=True)}
+                       for m in max_thresholds}).encode()
+    with open(path, "wb") as f:
+        f.write(zlib.compress(blob, 9))
+    return path
+
+
 def compiler():
     return "/usr/bin/g++" if os.access("/usr/bin/g++", os.X_OK) else "g++"
 

@@ -97,9 +97,12 @@ inline float convert_float(int v) { return (float)v; }
 inline float2 convert_float2(int2 v) { return mk_float2((float)v.x, (float)v.y); }
 inline float4 convert_float4(uchar4 v) { return mk_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w); }
 inline int2 convert_int2(float2 v) { return mk_int2((int)v.x, (int)v.y); }
-// out-of-range input is undefined in OpenCL C (no _sat); the restated oracle takes the low byte of
-// the truncated integer, and so does this layer
-inline uchar4 convert_uchar4(float4 v) { return mk_uchar4((uchar)(int)v.x, (uchar)(int)v.y, (uchar)(int)v.z, (uchar)(int)v.w); }
+// out-of-range input is undefined in OpenCL C (no _sat); this layer does what the one real OpenCL
+// device the kernels were run on does (NVIDIA OpenCL 3.0, B200: cvt.rzi.u8.f32 clamps, NaN -> 0)
+inline uchar cl_f2uchar_rtz(float v) { return v >= 255.0f ? (uchar)255 : (v > 0.0f ? (uchar)(int)v : (uchar)0); }
+inline uchar4 convert_uchar4(float4 v) {
+    return mk_uchar4(cl_f2uchar_rtz(v.x), cl_f2uchar_rtz(v.y), cl_f2uchar_rtz(v.z), cl_f2uchar_rtz(v.w));
+}
 
 // ---- reinterpretation ---------------------------------------------------------------------------
 template <class To, class From> inline To cl_bitcast(From f) {

@@ -108,3 +108,25 @@ def test_live_pictures(rasterizers):
 def test_live_s4b_full_size(rasterizers):
     """BASELINE.json's '100k curves at 3840x2160' (S4b) against the reference kernels, every pixel."""
     live(rasterizers(CANONICAL_SPEC), scenes.s4b())
+
+
+OPENCL = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "opencl_b200_hashes.json")))["strict"]
+
+
+@pytest.mark.parametrize("name", ["s2", "s4b", "s4"])
+def test_full_size_scenes_against_the_real_opencl_run(rasterizers, name):
+    """The CUDA path against what the reference's kernels produced under NVIDIA's OpenCL runtime on a
+    B200 (tests/golden/opencl_b200_hashes.json, IEEE build; s2's entry comes from the reference-options
+    build and is not used): same image hash, same threshold total, GPU-binned (level 2)."""
+    import hashlib
+    if name not in OPENCL:
+        pytest.skip("not in the IEEE OpenCL run")
+    img, stats = rasterizers(CANONICAL_SPEC).raster_scene(0, getattr(scenes, name)())
+    assert stats.n_thresholds == OPENCL[name]["thresholds"]
+    assert hashlib.sha256(img.astype("<u4").tobytes()).hexdigest() == OPENCL[name]["sha256"]
+
+
+def test_golden_files_agree():
+    """The vectors from the compiled-for-host reference and from the OpenCL run on the B200 are the same."""
+    for name in SCENES:
+        assert GOLDEN[name] == OPENCL[name], name

@@ -204,3 +204,47 @@ def test_reference_golden_images_verbatim():
     stored = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_images.npz"))
     for name in VERBATIM:
         assert np.array_equal(render(name, reference=False).image, stored[name]), name
+
+
+def _opencl_hashes():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "opencl_b200_hashes.json")))
+
+
+def test_oracle_matches_vectors_from_a_real_opencl_run():
+    """tests/golden/opencl_b200_hashes.json was written on the GPU box by oracle/refbuild/ocl_run.py: the
+    reference's Kernels.cl, verbatim, compiled and run by NVIDIA's OpenCL 3.0 runtime on the B200
+    ("strict": FP_CONTRACT OFF + correctly rounded divide, i.e. IEEE like the oracle).  Image, threshold
+    total, per-thread counts and shape bits of the oracle hash to the same values — small scenes here,
+    S2/S4b/S4 at full size below."""
+    from golden.make_golden import SCENES, digest, render
+    strict = _opencl_hashes()["strict"]
+    for name in SCENES:
+        assert digest(render(name, reference=False)) == strict[name], name
+    extra = {"fuzzy_circles_2000": scenes.fuzzy_circles(2000, 640, 480, 5, 50, 0x5EED),
+             "random_rectangles_300": scenes.random_rectangles(300, 640, 480, 5)}
+    for name, scene in extra.items():
+        assert digest(oracle.render(scene)) == strict[name], name
+
+
+@pytest.mark.parametrize("name", ["s4b", "s4"])
+def test_oracle_matches_real_opencl_run_at_full_size(name):
+    """BASELINE.json's 3840x2160 configurations: S4b (100k curves) and S4 (100k circles, 14.1 M thresholds)."""
+    from golden.make_golden import digest
+    strict = _opencl_hashes()["strict"]
+    assert digest(oracle.render(getattr(scenes, name)())) == strict[name]
+
+
+def test_reference_build_options_stay_within_the_north_star_tolerance():
+    """Under the reference's own options (-cl-fast-relaxed-math) the same OpenCL run differs from the IEEE
+    one by at most 1/255 on any channel; recorded by ocl_run.py in profiles/r1_opencl_reference.json."""
+    import json
+    import os
+    prof = json.load(open(os.path.join(os.path.dirname(__file__), "..", "profiles", "r1_opencl_reference.json")))
+    for name, r in prof["results"]["reference"].items():
+        assert r["max_channel_diff"] <= 1 and r["shape_bits_equal"], name
+        if name in ("s2", "s3", "s4b", "s4"):
+            assert r["exact_rate"] >= 0.999, name
+    for name, r in prof["results"]["strict"].items():
+        assert r["digest_equals_oracle"] and r["pixels_differing"] == 0, name
