@@ -141,6 +141,39 @@ def oracle_frame_sampler(scene, budget_s=12.0, kind=None):
     return run, desc
 
 
+def opencl_reference_on_this_gpu(workload, timeout_s=150):
+    """Side measurement, not an arm: the reference's Kernels.cl, verbatim, under the OpenCL runtime of the
+    GPU box (NVIDIA OpenCL on the same B200), same scene, same raster jobs — oracle/refbuild/ocl_run.py in a
+    child process with a time limit.  Needs oracle/_ref/ocl_program.bin (built where /root/reference
+    exists) and libnvidia-opencl on the box; says why when it cannot run."""
+    import tempfile
+    blob = os.path.join(ROOT, "oracle", "_ref", "ocl_program.bin")
+    if not os.path.exists(blob):
+        return {"unavailable": "oracle/_ref/ocl_program.bin not built (no reference tree at build time)"}
+    scene_key = WORKLOADS[workload][0]
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "ocl.json")
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "refbuild", "ocl_run.py"), "--out", out,
+               "--scenes", scene_key, "--variants", "reference", "--frames", "3"]
+        try:
+            subprocess.run(cmd, timeout=timeout_s, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False)
+            with open(out) as f:
+                log = json.load(f)
+            if scene_key not in log.get("results", {}).get("reference", {}):
+                last = log["steps"][-1] if log.get("steps") else {}
+                return {"unavailable": (str(last.get("error") or last.get("msg") or "no result"))[:200]}
+            res = log["results"]["reference"][scene_key]
+        except Exception as e:  # noqa: BLE001 - a side measurement never fails the bench
+            return {"unavailable": repr(e)[:200]}
+    return {"value": 1.0 / res["kernel_seconds"], "unit": "frames/s", "kernel_ms": res["kernel_seconds"] * 1e3,
+            "frame_ms_with_scratch_alloc": res["frame_seconds"] * 1e3, "frames_timed": res["frames_timed"],
+            "device": log.get("device", {}).get("name"), "runtime": log.get("device", {}).get("version"),
+            "options": "-cl-fast-relaxed-math -cl-strict-aliasing (OpenCL/Setup.hs:126-129)",
+            "timing": "wall clock around the three launches of every job, clFinish on both sides, best frame",
+            "pixels_vs_oracle": {"exact_rate": res["exact_rate"], "max_channel_diff": res["max_channel_diff"],
+                                 "threshold_counts_equal": res["threshold_counts_equal"]}}
+
+
 CPU_NOTES = {
     "reference": "the reference's own Kernels.cl compiled for the host (g++ -O3, IEEE f32, OpenMP over the NDRange, "
                  "scratch layout and three passes per job as in OpenCL/CallKernels.hs:88-179); tile tree restated "
@@ -430,6 +463,8 @@ def run_native(args, rank, world, local_rank):
                 # the restated port beside it: same arithmetic, tighter scratch layout and sort
                 run, desc = oracle_frame_sampler(scene, budget_s=6.0, kind="port")
                 line["cpu_baseline"]["port_value"] = 1.0 / run()
+            if not args.no_opencl_reference:
+                line["reference_opencl_same_gpu"] = opencl_reference_on_this_gpu(args.workload)
         print(json.dumps(line), flush=True)
     strips.close()
     dscene.free()
@@ -448,6 +483,8 @@ def main():
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary S4b reading")
+    ap.add_argument("--no-opencl-reference", action="store_true",
+                    help="skip the side measurement of the reference's kernels under OpenCL on this GPU")
     ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep the area-based strip partition")
     ap.add_argument("--gather-order", choices=("auto", "early", "late"), default="auto",
                     help="N > 1: post the presenting rank's receives before (early) or after (late) its own strip; auto measures both")

@@ -338,3 +338,55 @@ def thin_rectangles(n, width=64, height=None, spacing=1.0, thickness=0.5, skew=0
     if one_shape:
         b.shape(b.solid(0.1, 0.3, 0.6, 0.6), outlines)
     return b.freeze()
+
+
+def mixed_bag(n, width, height, seed, name=""):
+    """Seeded mix of everything the path distinguishes, for differential tests: free-form closed curves
+    with random control points (knobs to split, strands of every length, self-intersections), thin
+    slivers, rotated rectangles, circles, add/subtract pairs sharing a substance, opaque and translucent
+    solids, and picture substances with random placement and scale."""
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder(width, height, tuple(float(v) for v in rng.uniform(0, 1, 3)) + (1.0,),
+                     name=name or f"mixedBag-{n}-{width}x{height}-{seed}")
+    pictures = [b.picture(synthetic_picture(int(rng.integers(8, 90)), int(rng.integers(8, 70)), int(seed) + k))
+                for k in range(2)]
+
+    def blob(cx, cy, radius, points):
+        ang = np.sort(rng.uniform(0, 2 * np.pi, points))
+        rad = radius * rng.uniform(0.35, 1.0, points)
+        on = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1)
+        mid = 0.5 * (on + np.roll(on, -1, axis=0))
+        off = mid + rng.normal(0, 0.45 * radius, (points, 2)) * (rng.uniform(size=(points, 1)) < 0.7)
+        return np.concatenate([on, off], axis=1).astype(np.float32)
+
+    for _ in range(n):
+        x, y = float(rng.uniform(-0.1 * width, 1.1 * width)), float(rng.uniform(-0.1 * height, 1.1 * height))
+        size = float(np.exp(rng.uniform(np.log(0.4), np.log(0.45 * max(width, height)))))
+        use_picture = rng.uniform() < 0.15
+        if use_picture:
+            sub = b.picture_substance(pictures[int(rng.integers(0, 2))], (x - size, y - size),
+                                      float(rng.choice([1.0, 1.0, 2.0, 0.5, 3.3])))
+        else:
+            alpha = 1.0 if rng.uniform() < 0.3 else float(rng.uniform(0.05, 0.95))
+            sub = b.solid(*(float(v) for v in rng.uniform(0, 1, 3)), alpha)
+        kind = int(rng.integers(0, 6))
+        if kind == 0:
+            b.shape(sub, [blob(x, y, size, int(rng.integers(3, 24)))], is_picture=use_picture)
+        elif kind == 1:      # a hole cut by a second, subtracting shape of the same substance (listed first = on top)
+            b.shape(sub, [blob(x, y, 0.5 * size, int(rng.integers(3, 9)))], subtract=True, is_picture=use_picture)
+            b.shape(sub, [blob(x, y, size, int(rng.integers(3, 12)))], is_picture=use_picture)
+        elif kind == 2:      # two outlines in one shape (even-odd between them)
+            b.shape(sub, [blob(x, y, size, int(rng.integers(3, 10))), blob(x, y, 0.6 * size, int(rng.integers(3, 10)))],
+                    is_picture=use_picture)
+        elif kind == 3 and not use_picture:
+            b.rectangle(sub, float(rng.uniform(0.05, 2.0) * size), float(rng.uniform(0.05, 2.0) * size),
+                        [("translate", x, y), ("rotate", float(rng.uniform(0, 1)))])
+        elif kind == 4 and not use_picture:
+            b.circle(sub, [("translate", x, y), ("scale", size)])
+        else:                # sliver: a long triangle thinner than a pixel
+            ang = float(rng.uniform(0, 2 * np.pi))
+            d = np.array([np.cos(ang), np.sin(ang)]) * size * 3
+            nrm = np.array([-np.sin(ang), np.cos(ang)]) * float(rng.uniform(0.05, 0.8))
+            b.shape(sub, [_straight_outline([(x, y), (x + d[0], y + d[1]), (x + d[0] + nrm[0], y + d[1] + nrm[1])])],
+                    is_picture=use_picture)
+    return b.freeze()

@@ -35,3 +35,13 @@ def test_rotated_rectangles_and_cutouts(rasterizer, case):
 def test_opaque_layers_stop_the_compositing_chain(rasterizer):
     # every shape opaque: determineColor stops at the first layer (alpha == 1), stacks still differ
     level2_parity(rasterizer, scenes.random_rectangles(200, 500, 300, 77, alpha=(1.0, 1.0)))
+
+
+@pytest.mark.parametrize("case", range(10))
+def test_mixed_bag(rasterizer, case):
+    """Free-form curves with random control points (knobs, self-intersections), slivers, holes, two-outline
+    shapes, pictures at several scales — the scenes tests/test_reference_pin.py holds the oracle to the
+    reference's own kernels on."""
+    rng = np.random.default_rng(5000 + case)
+    w, h = int(rng.integers(20, 700)), int(rng.integers(20, 500))
+    level2_parity(rasterizer, scenes.mixed_bag(int(rng.integers(1, 300)), w, h, 7000 + case))

@@ -118,3 +118,13 @@ def test_s4b_full_size():
     mine, ref = both(scenes.s4b())
     assert_identical(mine, ref)
     assert mine.total_thresholds == 744366
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_mixed_bag(case):
+    """Free-form curves with random control points (knobs, self-intersections), slivers, holes, two-outline
+    shapes, rotated rectangles, pictures at several scales, on awkward canvases, two RasterSpecs."""
+    rng = np.random.default_rng(5000 + case)
+    w, h = int(rng.integers(20, 700)), int(rng.integers(20, 500))
+    scene = scenes.mixed_bag(int(rng.integers(1, 300)), w, h, 7000 + case)
+    assert_identical(*both(scene, SPEC_64 if case % 3 == 0 else None))
