@@ -141,6 +141,55 @@ def oracle_frame_sampler(scene, budget_s=12.0, kind=None):
     return run, desc
 
 
+def level3_reading(r, scene, dscene, stream, flush, torch):
+    """Secondary reading, not part of `value`: the same frame entered one level higher,
+    from the scene BEFORE serialisation — outlines + transformer stacks (S4: one 17-pair outline, 100,000
+    placements) — with the strands built on the GPU.  Device-resident (CUDA events, L2 flushed) and end to end
+    with host buffers; beside it the harness's single-core serialisation of the same scene, which is what the
+    Haskell front end does per frame today."""
+    dscene.put_outlines()
+    ms, strands_ms = [], []
+    for i in range(3 + 10):
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        r.frame_begin_device_outlines(dscene, i)
+        r.raster_outlines_device(dscene)
+        _, st = r.frame_end(want_image=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if i >= 3:
+            ms.append(e0.elapsed_time(e1))
+            strands_ms.append(st.ms_strands)
+    host_img = np.empty((scene.height, scene.width), dtype=np.uint32)
+    arrays = [np.ascontiguousarray(a) for a in scene.raw] + [scene.substances, host_img]
+    scene.raw = tuple(arrays[:4])
+    for a in arrays:
+        r.host_register(a)
+    e2e = []
+    for i in range(2 + 5):
+        t0 = time.perf_counter()
+        r.raster_outlines(i, scene, out=host_img)
+        if i >= 2:
+            e2e.append(time.perf_counter() - t0)
+    for a in arrays:
+        r.host_unregister(a)
+    from gudni_b200 import scenes as scene_factories
+    t0 = time.perf_counter()
+    scene_factories.s4()
+    t_host = time.perf_counter() - t0
+    h2d = sum(a.nbytes for a in arrays[:5]) + scene.picture_bytes.nbytes + scene.picture_uses.nbytes
+    return {"value": 1e3 / float(np.mean(ms)), "unit": "frames/s", "ms_per_step": float(np.mean(ms)),
+            "ms_strands": float(np.mean(strands_ms)),
+            "strand_kernels": "strand_measure_kernel + strand_scan_kernel + strand_emit_kernel",
+            "strand_bytes": {"in": int(sum(a.nbytes for a in arrays[:4])), "out": int(scene.geometry.nbytes + scene.entries.nbytes)},
+            "strand_gbs": (sum(a.nbytes for a in arrays[:4]) + scene.geometry.nbytes + scene.entries.nbytes) / (float(np.mean(strands_ms)) * 1e-3) / 1e9,
+            "e2e": {"value": 1.0 / float(np.mean(e2e)), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(host_img.nbytes)},
+            "host_serialisation_ms_1_core": t_host * 1e3}
+
+
 def opencl_reference_on_this_gpu(workload, timeout_s=150):
     """Side measurement, not an arm: the reference's Kernels.cl, verbatim, under the OpenCL runtime of the
     GPU box (NVIDIA OpenCL on the same B200), same scene, same raster jobs — oracle/refbuild/ocl_run.py in a
@@ -452,6 +501,11 @@ def run_native(args, rank, world, local_rank):
                                     "ms_per_step": float(np.mean(tb)),
                                     "mpixel_per_s": sb.width * sb.height * 1e3 / float(np.mean(tb)) / 1e6}}
             sr.close(); db.free()
+        if world == 1 and args.workload == "S4" and not args.no_also:
+            try:
+                line["also"]["level3_outlines_in"] = level3_reading(r, scene, dscene, stream, flush, torch)
+            except Exception as e:  # noqa: BLE001 - a secondary reading never fails the bench
+                line["also"]["level3_outlines_in"] = {"unavailable": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle
             kind = cpu_kind()

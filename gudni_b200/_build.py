@@ -80,3 +80,20 @@ def build_reference(force=False, verbose=False):
         sys.path.insert(0, REPO)
     from oracle.refbuild import build_ref
     return build_ref.build(force=force, verbose=verbose)
+
+
+LIB_STRAND_CHECK = os.path.join(REPO, "tests", "native", "libstrand_check.so")
+
+
+def build_strand_check(force=False, verbose=False):
+    """tests/native/libstrand_check.so: the level-3 kernels' per-shape logic (csrc/strand_build.cuh)
+    compiled for the host — a test helper, see tests/native/strand_check.cpp."""
+    src = os.path.join(REPO, "tests", "native", "strand_check.cpp")
+    deps = [src, os.path.join(CSRC, "strand_build.cuh"), os.path.join(REPO, "include", "gudni_b200.h")]
+    if not force and _newer(LIB_STRAND_CHECK, deps):
+        return LIB_STRAND_CHECK
+    cmd = [_host_cxx(), "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", LIB_STRAND_CHECK, src]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_STRAND_CHECK

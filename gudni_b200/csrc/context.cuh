@@ -75,13 +75,20 @@ struct gudni_ctx {
     DevBuf binWork[8];
     DevBuf binCounters;
 
+    // strand building (level 3)
+    DevBuf olShapes, olOutlines, olPairs, olTransforms;   // uploaded outline data (host-pointer variant)
+    DevBuf strandMeasures, strandScan, strandTotals;
+    int64_t builtStrands = 0;
+    int64_t outlineInputBytes = 0;
+    bool strandsUsed = false;
+
     // pinned staging for host transfers
     void* pinned = nullptr;
     size_t pinnedCap = 0;
 
     // timing
     cudaEvent_t evFrameBegin = nullptr, evUploadDone = nullptr, evBinDone = nullptr, evRasterDone = nullptr,
-                evDownloadDone = nullptr, evFirstKernel = nullptr;
+                evDownloadDone = nullptr, evFirstKernel = nullptr, evStrandsDone = nullptr;
     bool firstKernelRecorded = false;
     float lastFrameMs = 0.f;
     gudni_stats lastStats{};

@@ -60,6 +60,43 @@ struct Scene {
     std::vector<int> pictureOffsets, pictureW, pictureH;
     int64_t culled = 0, curves = 0;
 
+    // The same scene BEFORE serialisation, as level 3 of the ABI takes it (gudni_b200_raster_outlines):
+    // every shape with its untransformed outlines and its transformer stack, culled ones included.
+    std::vector<gudni_outline_shape> rawShapes;
+    std::vector<gudni_outline> rawOutlines;
+    std::vector<gudni_curve_pair> rawPairs;
+    std::vector<gudni_transform> rawTransforms;
+    int rawUnitCircle = -1;   // outline index shared by every circle
+
+    int rawAddOutline(const Outline& o) {
+        gudni_outline r{(uint32_t)rawPairs.size(), (uint32_t)o.size()};
+        for (const CurvePair& p : o) rawPairs.push_back({p.on.x, p.on.y, p.off.x, p.off.y});
+        rawOutlines.push_back(r);
+        return (int)rawOutlines.size() - 1;
+    }
+    static uint64_t makeTag(int substance, bool isPicture, bool subtract) {
+        return (isPicture ? GUDNI_TAG_SUBSTANCE_PICTURE : GUDNI_TAG_SUBSTANCE_SOLID) |
+               (subtract ? GUDNI_TAG_COMPOUND_SUBTRACT : GUDNI_TAG_COMPOUND_ADD) |
+               ((uint64_t)substance & GUDNI_TAG_SUBSTANCEID_MASK);
+    }
+    void rawAddShape(int substance, bool isPicture, bool subtract, int firstOutline, int nOutlines,
+                     const std::vector<Transform>& stack) {
+        gudni_outline_shape r{};
+        r.tag = makeTag(substance, isPicture, subtract);
+        r.first_outline = (uint32_t)firstOutline;
+        r.n_outlines = (uint32_t)nOutlines;
+        r.first_transform = (uint32_t)rawTransforms.size();
+        r.n_transforms = (uint32_t)stack.size();
+        for (const Transform& t : stack) {
+            gudni_transform g{};
+            if (t.kind == Transform::Translate) { g.kind = GUDNI_TRANSFORM_TRANSLATE; g.a = t.delta.x; g.b = t.delta.y; }
+            else if (t.kind == Transform::Scale) { g.kind = GUDNI_TRANSFORM_SCALE; g.a = t.factor; }
+            else { g.kind = GUDNI_TRANSFORM_ROTATE; g.a = std::cos(t.factor); g.b = std::sin(t.factor); }   // as rotatePoint
+            rawTransforms.push_back(g);
+        }
+        rawShapes.push_back(r);
+    }
+
     // onSubstance (Raster/Serialize.hs:216-262), Solid branch.
     int addSolid(float r, float g, float b, float a) {
         substances.insert(substances.end(), {r, g, b, a});
@@ -112,9 +149,7 @@ struct Scene {
         for (const Outline& o : outlines) outlineToStrands(o, strands);
         // appendGeoRef (:76-85): start measured in 16-byte units
         gudni_shape_entry e{};
-        e.tag = (isPicture ? GUDNI_TAG_SUBSTANCE_PICTURE : GUDNI_TAG_SUBSTANCE_SOLID) |
-                (subtract ? GUDNI_TAG_COMPOUND_SUBTRACT : GUDNI_TAG_COMPOUND_ADD) |
-                ((uint64_t)substance & GUDNI_TAG_SUBSTANCEID_MASK);
+        e.tag = makeTag(substance, isPicture, subtract);
         e.geo_start = (uint32_t)(geometry.size() / 16);
         e.num_strands = (uint32_t)strands.size();
         e.left = l; e.top = t; e.right = r; e.bottom = b;
@@ -154,7 +189,11 @@ void gs_add_shape(void* h, int substance, int is_picture, int subtract, const fl
         outlines[i].resize(outline_sizes[i]);
         for (int k = 0; k < outline_sizes[i]; k++, p += 4) outlines[i][k] = {{p[0], p[1]}, {p[2], p[3]}};
     }
-    static_cast<Scene*>(h)->addShape(substance, is_picture != 0, subtract != 0, outlines);
+    Scene* s = static_cast<Scene*>(h);
+    const int first = (int)s->rawOutlines.size();
+    for (const Outline& o : outlines) s->rawAddOutline(o);
+    s->rawAddShape(substance, is_picture != 0, subtract != 0, first, n_outlines, {});   // already transformed
+    s->addShape(substance, is_picture != 0, subtract != 0, outlines);
 }
 
 // Layout/Draw.hs rectangle / circle run through a transformer stack given outermost first as
@@ -170,12 +209,19 @@ static std::vector<Transform> parseStack(const float* stack, int n) {
     return t;
 }
 void gs_add_rectangle(void* h, int substance, int subtract, float w, float hgt, const float* stack, int n_stack) {
-    Outline o = transformOutline(parseStack(stack, n_stack), rectangleOutline(w, hgt));
-    static_cast<Scene*>(h)->addShape(substance, false, subtract != 0, {o});
+    Scene* s = static_cast<Scene*>(h);
+    const std::vector<Transform> st = parseStack(stack, n_stack);
+    s->rawAddShape(substance, false, subtract != 0, s->rawAddOutline(rectangleOutline(w, hgt)), 1, st);
+    Outline o = transformOutline(st, rectangleOutline(w, hgt));
+    s->addShape(substance, false, subtract != 0, {o});
 }
 void gs_add_circle(void* h, int substance, int is_picture, int subtract, const float* stack, int n_stack) {
-    Outline o = transformOutline(parseStack(stack, n_stack), circleOutline());
-    static_cast<Scene*>(h)->addShape(substance, is_picture != 0, subtract != 0, {o});
+    Scene* s = static_cast<Scene*>(h);
+    const std::vector<Transform> st = parseStack(stack, n_stack);
+    if (s->rawUnitCircle < 0) s->rawUnitCircle = s->rawAddOutline(circleOutline());
+    s->rawAddShape(substance, is_picture != 0, subtract != 0, s->rawUnitCircle, 1, st);
+    Outline o = transformOutline(st, circleOutline());
+    s->addShape(substance, is_picture != 0, subtract != 0, {o});
 }
 // Number of curve pairs of the unit circle outline followed by the pairs themselves (for Python).
 int gs_unit_circle(float* pairs, int capacity) {
@@ -213,7 +259,10 @@ void gs_add_fuzzy_circles(void* h, int n, float range_w, float range_h, float mi
         float rgb[3];
         hslToRgb(hue, sat, light, rgb);
         int sub = s->addSolid(rgb[0], rgb[1], rgb[2], alpha);
-        Outline o = transformOutline({Transform::translate(px, py), Transform::scale(radius)}, unit);
+        const std::vector<Transform> st{Transform::translate(px, py), Transform::scale(radius)};
+        if (s->rawUnitCircle < 0) s->rawUnitCircle = s->rawAddOutline(unit);
+        s->rawAddShape(sub, false, false, s->rawUnitCircle, 1, st);
+        Outline o = transformOutline(st, unit);
         s->addShape(sub, false, false, {o});
     }
 }
@@ -244,6 +293,11 @@ const void* gs_picture_uses(void* h, int* n) {
     *n = (int)s->pictureUses.size();
     return s->pictureUses.data();
 }
+// the scene before serialisation (level 3 inputs)
+const void* gs_raw_shapes(void* h, int* n) { Scene* s = static_cast<Scene*>(h); *n = (int)s->rawShapes.size(); return s->rawShapes.data(); }
+const void* gs_raw_outlines(void* h, int* n) { Scene* s = static_cast<Scene*>(h); *n = (int)s->rawOutlines.size(); return s->rawOutlines.data(); }
+const void* gs_raw_pairs(void* h, int* n) { Scene* s = static_cast<Scene*>(h); *n = (int)s->rawPairs.size(); return s->rawPairs.data(); }
+const void* gs_raw_transforms(void* h, int* n) { Scene* s = static_cast<Scene*>(h); *n = (int)s->rawTransforms.size(); return s->rawTransforms.data(); }
 void gs_info(void* h, int* width, int* height, float* background, int64_t* culled, int64_t* curves) {
     Scene* s = static_cast<Scene*>(h);
     *width = s->width;

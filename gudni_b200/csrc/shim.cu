@@ -8,6 +8,7 @@
 #include "binning.cuh"
 #include "context.cuh"
 #include "raster_kernels.cuh"
+#include "strands.cuh"
 
 using gudni_dev::FrameParams;
 
@@ -110,6 +111,7 @@ int beginFrameCommon(gudni_ctx* ctx, const float bg[4], int width, int height, i
     ctx->rasteredShapes = 0;
     ctx->firstKernelRecorded = false;
     ctx->binUsed = false;
+    ctx->strandsUsed = false;
     ctx->inFrame = true;
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, 256, ctx->stream));
     return GUDNI_OK;
@@ -158,9 +160,10 @@ int gudni_b200_init(int device, const gudni_spec* want, gudni_spec* got, gudni_c
     ctx->stream = ctx->ownStream;
     if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
     cudaEvent_t* evs[] = {&ctx->evFrameBegin, &ctx->evUploadDone, &ctx->evBinDone, &ctx->evRasterDone,
-                          &ctx->evDownloadDone, &ctx->evFirstKernel};
+                          &ctx->evDownloadDone, &ctx->evFirstKernel, &ctx->evStrandsDone};
     for (cudaEvent_t* e : evs)
         if (cudaEventCreate(e) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
+    if (gudni_launch::strandTableInit(ctx) != GUDNI_OK) return fail(GUDNI_ERR_CUDA);
     if (devEnsure(ctx, ctx->counters, gudni_dev::kCountersBytes) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
     ctx->spillCapacity = kSpillListCapacity;
     if (devEnsure(ctx, ctx->spillList, (size_t)kSpillListCapacity * 8) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
@@ -178,14 +181,15 @@ void gudni_b200_destroy(gudni_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->geometry, &ctx->substances, &ctx->pictures, &ctx->pictureUses, &ctx->shapes, &ctx->tiles,
                       &ctx->tileThreadBase, &ctx->frame, &ctx->counters, &ctx->spillList, &ctx->spillThr, &ctx->spillHdr,
                       &ctx->dbgThresholds, &ctx->dbgShapeBits, &ctx->entries, &ctx->binCounters, &ctx->thrStore, &ctx->hdrStore,
-                      &ctx->threadRecs, &ctx->strandBounds, &ctx->tileOrder};
+                      &ctx->threadRecs, &ctx->strandBounds, &ctx->tileOrder, &ctx->olShapes, &ctx->olOutlines, &ctx->olPairs,
+                      &ctx->olTransforms, &ctx->strandMeasures, &ctx->strandScan, &ctx->strandTotals};
     for (DevBuf* b : bufs)
         if (b->ptr) cudaFree(b->ptr);
     for (DevBuf& b : ctx->binWork)
         if (b.ptr) cudaFree(b.ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEvent_t evs[] = {ctx->evFrameBegin, ctx->evUploadDone, ctx->evBinDone, ctx->evRasterDone, ctx->evDownloadDone,
-                         ctx->evFirstKernel};
+                         ctx->evFirstKernel, ctx->evStrandsDone};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
@@ -359,6 +363,86 @@ int gudni_b200_raster_scene_device(gudni_ctx* ctx, const void* dev_entries, int 
     return rasterSceneCommon(ctx, dev_entries, n_entries);
 }
 
+// onShape's geometry work + enclose + outlineToStrands (Raster/Serialize.hs:148-177, Enclosure.hs:62-73,
+// Strand.hs:153-178), then level 2
+static int rasterOutlinesCommon(gudni_ctx* ctx, const void* devShapes, int n_shapes, const void* devOutlines,
+                                const void* devPairs, const void* devTransforms, int64_t inputBytes) {
+    GUDNI_TRY(ensureFrameBuffer(ctx));
+    markFirstKernel(ctx);
+    GUDNI_TRY(gudni_launch::buildStrands(ctx, devShapes, n_shapes, devOutlines, devPairs, devTransforms));
+    GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evStrandsDone, ctx->stream));
+    ctx->strandsUsed = true;
+    ctx->outlineInputBytes = inputBytes;
+    return rasterSceneCommon(ctx, ctx->entries.ptr, ctx->nEntries);
+}
+
+int gudni_b200_raster_outlines(gudni_ctx* ctx, const gudni_outline_shape* shapes, int n_shapes, const gudni_outline* outlines,
+                               int n_outlines, const gudni_curve_pair* pairs, int64_t n_pairs,
+                               const gudni_transform* transforms, int n_transforms) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if (!ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_outlines outside a frame");
+    if (ctx->nTiles) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_outlines after other raster calls of the frame");
+    if (n_shapes < 0 || n_outlines < 0 || n_pairs < 0 || n_transforms < 0 || (n_shapes && !shapes) ||
+        (n_outlines && !outlines) || (n_pairs && !pairs) || (n_transforms && !transforms))
+        return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_outlines: null or negative-sized input");
+    if (n_pairs >= (1ll << 32)) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_outlines: more than 2^32 curve pairs");
+    // the kernels index with these: check every slice once on the host
+    for (int i = 0; i < n_outlines; i++)
+        if ((uint64_t)outlines[i].first_pair + outlines[i].n_pairs > (uint64_t)n_pairs)
+            return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_outlines: outline %d runs past the pair array", i);
+    for (int i = 0; i < n_shapes; i++) {
+        if ((uint64_t)shapes[i].first_outline + shapes[i].n_outlines > (uint64_t)n_outlines)
+            return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_outlines: shape %d outline slice out of range", i);
+        if ((uint64_t)shapes[i].first_transform + shapes[i].n_transforms > (uint64_t)n_transforms)
+            return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_outlines: shape %d transform slice out of range", i);
+    }
+    for (int i = 0; i < n_transforms; i++)
+        if (transforms[i].kind > GUDNI_TRANSFORM_ROTATE)
+            return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_outlines: transform %d has unknown kind %u", i, transforms[i].kind);
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GUDNI_TRY(uploadTo(ctx, ctx->olShapes, shapes, (size_t)n_shapes * sizeof(gudni_outline_shape)));
+    GUDNI_TRY(uploadTo(ctx, ctx->olOutlines, outlines, (size_t)n_outlines * sizeof(gudni_outline)));
+    GUDNI_TRY(uploadTo(ctx, ctx->olPairs, pairs, (size_t)n_pairs * sizeof(gudni_curve_pair)));
+    GUDNI_TRY(uploadTo(ctx, ctx->olTransforms, transforms, (size_t)n_transforms * sizeof(gudni_transform)));
+    const int64_t inputBytes = (int64_t)n_shapes * 32 + (int64_t)n_outlines * 8 + n_pairs * 16 + (int64_t)n_transforms * 16;
+    return rasterOutlinesCommon(ctx, ctx->olShapes.ptr, n_shapes, ctx->olOutlines.ptr, ctx->olPairs.ptr, ctx->olTransforms.ptr,
+                                inputBytes);
+}
+
+int gudni_b200_raster_outlines_device(gudni_ctx* ctx, const void* dev_shapes, int n_shapes, const void* dev_outlines,
+                                      int n_outlines, const void* dev_pairs, int64_t n_pairs, const void* dev_transforms,
+                                      int n_transforms) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if (!ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_outlines outside a frame");
+    if (ctx->nTiles) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_outlines after other raster calls of the frame");
+    if (n_shapes < 0 || n_outlines < 0 || n_pairs < 0 || n_transforms < 0 || (n_shapes && (!dev_shapes || !dev_outlines || !dev_pairs)))
+        return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_outlines: null or negative-sized input");
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t inputBytes = (int64_t)n_shapes * 32 + (int64_t)n_outlines * 8 + n_pairs * 16 + (int64_t)n_transforms * 16;
+    return rasterOutlinesCommon(ctx, dev_shapes, n_shapes, dev_outlines, dev_pairs, dev_transforms, inputBytes);
+}
+
+int gudni_b200_debug_strands(gudni_ctx* ctx, void* geometry, size_t geometry_capacity, size_t* geometry_bytes,
+                             gudni_shape_entry* entries, int64_t entry_capacity, int64_t* n_entries) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (geometry_bytes) *geometry_bytes = ctx->geometryBytes;
+    if (n_entries) *n_entries = ctx->nEntries;
+    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (geometry) {
+        if (geometry_capacity < ctx->geometryBytes) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "debug_strands: geometry buffer too small");
+        if (ctx->geometryBytes)
+            GUDNI_CUDA_TRY(ctx, cudaMemcpy(geometry, ctx->geometryPtr, ctx->geometryBytes, cudaMemcpyDeviceToHost));
+    }
+    if (entries) {
+        if (entry_capacity < ctx->nEntries) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "debug_strands: entry buffer too small");
+        if (ctx->nEntries)
+            GUDNI_CUDA_TRY(ctx, cudaMemcpy(entries, ctx->entries.ptr, (size_t)ctx->nEntries * sizeof(gudni_shape_entry),
+                                           cudaMemcpyDeviceToHost));
+    }
+    return GUDNI_OK;
+}
+
 // OutputPtr read-back, OpenCL/Instances.hs:60-75
 int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats) {
     if (!ctx) return GUDNI_ERR_ARGUMENT;
@@ -408,11 +492,18 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     cudaEventElapsedTime(&s.ms_raster, ctx->evFirstKernel, ctx->evRasterDone);
     cudaEventElapsedTime(&s.ms_download, ctx->evRasterDone, ctx->evDownloadDone);
     s.ms_bin = 0.f;
+    s.ms_strands = 0.f;
     if (ctx->binUsed) {
         cudaEventElapsedTime(&s.ms_bin, ctx->evFirstKernel, ctx->evBinDone);
         s.ms_raster -= s.ms_bin;
     }
-    ctx->lastFrameMs = s.ms_raster + s.ms_bin;
+    if (ctx->strandsUsed) {       // level 3: first kernel .. strands done .. bin done .. raster done
+        cudaEventElapsedTime(&s.ms_strands, ctx->evFirstKernel, ctx->evStrandsDone);
+        s.ms_bin -= s.ms_strands;
+        // the outline data is what crosses the boundary instead of the geometry heap it becomes
+        s.algorithmic_bytes += ctx->outlineInputBytes + 32 * (int64_t)ctx->nEntries;
+    }
+    ctx->lastFrameMs = s.ms_raster + s.ms_bin + s.ms_strands;
     ctx->lastStats = s;
     if (stats) *stats = s;
     return GUDNI_OK;

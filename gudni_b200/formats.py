@@ -20,6 +20,14 @@ ENTRY_DTYPE = np.dtype([("tag", "<u8"), ("geo_start", "<u4"), ("num_strands", "<
 # PictureUsage PictureMemoryReference — Figure/Picture.hs:183-199, Kernels.cl:349-354 (24 B)
 PICTURE_USE_DTYPE = np.dtype([("translate_x", "<f4"), ("translate_y", "<f4"), ("width", "<i4"),
                               ("height", "<i4"), ("mem_offset", "<u4"), ("scale", "<f4")])
+# level 3 inputs, include/gudni_b200.h gudni_outline_shape / gudni_outline / gudni_curve_pair / gudni_transform
+OUTLINE_SHAPE_DTYPE = np.dtype([("tag", "<u8"), ("first_outline", "<u4"), ("n_outlines", "<u4"),
+                                ("first_transform", "<u4"), ("n_transforms", "<u4"), ("reserved", "<u4", (2,))])
+OUTLINE_DTYPE = np.dtype([("first_pair", "<u4"), ("n_pairs", "<u4")])
+CURVE_PAIR_DTYPE = np.dtype([("on_x", "<f4"), ("on_y", "<f4"), ("off_x", "<f4"), ("off_y", "<f4")])
+TRANSFORM_DTYPE = np.dtype([("kind", "<u4"), ("a", "<f4"), ("b", "<f4"), ("reserved", "<u4")])
+assert OUTLINE_SHAPE_DTYPE.itemsize == 32 and OUTLINE_DTYPE.itemsize == 8
+assert CURVE_PAIR_DTYPE.itemsize == 16 and TRANSFORM_DTYPE.itemsize == 16
 assert SHAPE_DTYPE.itemsize == 16 and TILE_DTYPE.itemsize == 32
 assert ENTRY_DTYPE.itemsize == 32 and PICTURE_USE_DTYPE.itemsize == 24
 
@@ -43,7 +51,8 @@ class CStats(ctypes.Structure):
                 ("n_thresholds", ctypes.c_int64), ("n_spilled_threads", ctypes.c_int64),
                 ("n_overflow_threads", ctypes.c_int64), ("algorithmic_bytes", ctypes.c_int64),
                 ("ms_upload", ctypes.c_float), ("ms_bin", ctypes.c_float),
-                ("ms_raster", ctypes.c_float), ("ms_download", ctypes.c_float)]
+                ("ms_raster", ctypes.c_float), ("ms_download", ctypes.c_float),
+                ("ms_strands", ctypes.c_float), ("reserved", ctypes.c_float)]
 
 
 @dataclass(frozen=True)

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 from . import _build
-from .formats import CSpec, CStats, RasterSpec, CANONICAL_SPEC, SHAPE_DTYPE, TILE_DTYPE
+from .formats import CSpec, CStats, RasterSpec, CANONICAL_SPEC, SHAPE_DTYPE, TILE_DTYPE, ENTRY_DTYPE
 
 _lib = None
 
@@ -28,7 +28,8 @@ ABI_SYMBOLS = [
     "gudni_b200_raster_scene", "gudni_b200_frame_end", "gudni_b200_frame_device_ptr", "gudni_b200_frame_target",
     "gudni_b200_ipc_export_frame", "gudni_b200_ipc_open", "gudni_b200_ipc_close", "gudni_b200_device_alloc",
     "gudni_b200_device_free", "gudni_b200_host_register", "gudni_b200_host_unregister", "gudni_b200_upload", "gudni_b200_download", "gudni_b200_frame_begin_device",
-    "gudni_b200_raster_scene_device", "gudni_b200_sync", "gudni_b200_last_frame_ms", "gudni_b200_launch_count",
+    "gudni_b200_raster_scene_device", "gudni_b200_raster_outlines", "gudni_b200_raster_outlines_device",
+    "gudni_b200_debug_strands", "gudni_b200_sync", "gudni_b200_last_frame_ms", "gudni_b200_launch_count",
     "gudni_b200_set_stream", "gudni_b200_debug_selftest", "gudni_b200_debug_enable", "gudni_b200_debug_thread_counts", "gudni_b200_debug_binned",
     "gudni_b200_last_error", "gudni_b200_destroy",
 ]
@@ -59,6 +60,9 @@ def load_library():
     L.gudni_b200_raster_job.argtypes = [vp, vp, i32, vp, i32, i32, i32]
     L.gudni_b200_raster_scene.argtypes = [vp, vp, i32]
     L.gudni_b200_raster_scene_device.argtypes = [vp, vp, i32]
+    L.gudni_b200_raster_outlines.argtypes = [vp, vp, i32, vp, i32, vp, i64, vp, i32]
+    L.gudni_b200_raster_outlines_device.argtypes = [vp, vp, i32, vp, i32, vp, i64, vp, i32]
+    L.gudni_b200_debug_strands.argtypes = [vp, vp, sz, c.POINTER(sz), vp, i64, c.POINTER(i64)]
     L.gudni_b200_frame_end.argtypes = [vp, vp, c.POINTER(CStats)]
     L.gudni_b200_frame_device_ptr.argtypes = [vp, c.POINTER(vp), c.POINTER(sz)]
     L.gudni_b200_frame_target.argtypes = [vp, vp, i32]
@@ -123,6 +127,12 @@ class DeviceScene:
             self.r._check(self.r._L.gudni_b200_upload(self.r._ctx, p, arr.ctypes.data, arr.nbytes))
         self._bufs.append(p)
         return p
+
+    def put_outlines(self):
+        """Upload the scene's pre-serialisation form (level 3 inputs); returns the four device pointers."""
+        self.outline_arrays = tuple(np.ascontiguousarray(a) for a in self.scene.raw)
+        self.outline_ptrs = tuple(self._put(a) for a in self.outline_arrays)
+        return self.outline_ptrs
 
     def put_entries(self, entries):
         """Upload one more shape-entry array (e.g. the entries of one chunk of a strip)."""
@@ -232,6 +242,53 @@ class Rasterizer:
             entries = scene.subset_rows(*rows)
         self.raster_entries(entries)
         return self.frame_end(out)
+
+    def frame_begin_outlines(self, scene, frame_count=0):
+        """frame_begin for level 3: everything but the geometry heap, which the library builds itself."""
+        s = np.ascontiguousarray(scene.substances, np.float32)
+        p = np.ascontiguousarray(scene.picture_bytes)
+        u = np.ascontiguousarray(scene.picture_uses)
+        bg = np.ascontiguousarray(scene.background, np.float32)
+        self._keep = (s, p, u, bg)
+        self._check(self._L.gudni_b200_frame_begin(self._ctx, None, 0, _ptr(s), len(s), _ptr(p), p.nbytes, _ptr(u), len(u),
+                                                   bg.ctypes.data, scene.width, scene.height, frame_count))
+        self._dims = (scene.height, scene.width)
+        self._rows = (0, scene.height)
+
+    def raster_outlines(self, frame_count, scene, out=None):
+        """Level 3: onShape's geometry work (transform, box, cull, strands: Raster/Serialize.hs:148-177,
+        Raster/Strand.hs:153-178) + tile binning + rasterization, all behind the shim.  `scene.raw` is the
+        scene before serialisation: (shapes, outlines, curve pairs, transforms)."""
+        self.frame_begin_outlines(scene, frame_count)
+        shapes, outlines, pairs, transforms = (np.ascontiguousarray(a) for a in scene.raw)
+        self._check(self._L.gudni_b200_raster_outlines(self._ctx, _ptr(shapes), len(shapes), _ptr(outlines), len(outlines),
+                                                       _ptr(pairs), len(pairs), _ptr(transforms), len(transforms)))
+        return self.frame_end(out)
+
+    def frame_begin_device_outlines(self, dscene: DeviceScene, frame_count=0):
+        sc = dscene.scene
+        bg = np.ascontiguousarray(sc.background, np.float32)
+        self._check(self._L.gudni_b200_frame_begin_device(
+            self._ctx, None, 0, dscene.substances, len(sc.substances), dscene.pictures, sc.picture_bytes.nbytes,
+            dscene.picture_uses, len(sc.picture_uses), bg.ctypes.data, sc.width, sc.height, frame_count))
+        self._dims = (sc.height, sc.width)
+        self._rows = (0, sc.height)
+
+    def raster_outlines_device(self, dscene: DeviceScene):
+        sh, ol, pr, tr = dscene.outline_ptrs
+        a = dscene.outline_arrays
+        self._check(self._L.gudni_b200_raster_outlines_device(self._ctx, sh, len(a[0]), ol, len(a[1]), pr, len(a[2]), tr,
+                                                              len(a[3])))
+
+    def debug_strands(self):
+        """Geometry heap and shape entries level 3 built for the last frame."""
+        nb, ne = ctypes.c_size_t(), ctypes.c_int64()
+        self._check(self._L.gudni_b200_debug_strands(self._ctx, None, 0, ctypes.byref(nb), None, 0, ctypes.byref(ne)))
+        geometry = np.empty(nb.value, np.uint8)
+        entries = np.empty(ne.value, ENTRY_DTYPE)
+        self._check(self._L.gudni_b200_debug_strands(self._ctx, _ptr(geometry), geometry.nbytes, ctypes.byref(nb),
+                                                     _ptr(entries), len(entries), ctypes.byref(ne)))
+        return geometry, entries
 
     # -- device-side access ----------------------------------------------------------------------
     def frame_device_ptr(self):

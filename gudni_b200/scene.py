@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 from . import _build
-from .formats import ENTRY_DTYPE, PICTURE_USE_DTYPE
+from .formats import (ENTRY_DTYPE, PICTURE_USE_DTYPE, OUTLINE_SHAPE_DTYPE, OUTLINE_DTYPE, CURVE_PAIR_DTYPE,
+                      TRANSFORM_DTYPE)
 
 _lib = None
 
@@ -40,7 +41,8 @@ def _load():
     for name in ("gs_geometry", "gs_picture_bytes"):
         getattr(lib, name).restype = c.c_void_p
         getattr(lib, name).argtypes = [c.c_void_p, c.POINTER(c.c_size_t)]
-    for name in ("gs_entries", "gs_substances", "gs_picture_uses"):
+    for name in ("gs_entries", "gs_substances", "gs_picture_uses", "gs_raw_shapes", "gs_raw_outlines", "gs_raw_pairs",
+                 "gs_raw_transforms"):
         getattr(lib, name).restype = c.c_void_p
         getattr(lib, name).argtypes = [c.c_void_p, c.POINTER(c.c_int)]
     lib.gs_info.argtypes = [c.c_void_p, c.POINTER(c.c_int), c.POINTER(c.c_int), fp,
@@ -64,7 +66,7 @@ class FrozenScene:
     """The byte buffers that cross the boundary, as numpy arrays."""
 
     def __init__(self, width, height, background, geometry, entries, substances, picture_bytes,
-                 picture_uses, culled=0, curves=0, name=""):
+                 picture_uses, culled=0, curves=0, name="", raw=None):
         self.width, self.height = int(width), int(height)
         self.background = np.asarray(background, dtype=np.float32)
         self.geometry = geometry
@@ -74,6 +76,8 @@ class FrozenScene:
         self.picture_uses = picture_uses
         self.culled, self.curves = int(culled), int(curves)
         self.name = name
+        # the scene before serialisation — (shapes, outlines, pairs, transforms) as level 3 takes them
+        self.raw = raw
 
     @property
     def n_shapes(self):
@@ -153,12 +157,17 @@ class SceneBuilder:
         picture_bytes = copy(p, nb.value, np.uint8)
         p = lib.gs_picture_uses(h, ctypes.byref(n))
         picture_uses = copy(p, n.value, PICTURE_USE_DTYPE)
+        raw = []
+        for getter, dtype in (("gs_raw_shapes", OUTLINE_SHAPE_DTYPE), ("gs_raw_outlines", OUTLINE_DTYPE),
+                              ("gs_raw_pairs", CURVE_PAIR_DTYPE), ("gs_raw_transforms", TRANSFORM_DTYPE)):
+            p = getattr(lib, getter)(h, ctypes.byref(n))
+            raw.append(copy(p, n.value, dtype))
         w, hh = ctypes.c_int(), ctypes.c_int()
         bg = (ctypes.c_float * 4)()
         culled, curves = ctypes.c_int64(), ctypes.c_int64()
         lib.gs_info(h, ctypes.byref(w), ctypes.byref(hh), bg, ctypes.byref(culled), ctypes.byref(curves))
         return FrozenScene(w.value, hh.value, list(bg), geometry, entries, substances, picture_bytes,
-                           picture_uses, culled.value, curves.value, self.name)
+                           picture_uses, culled.value, curves.value, self.name, tuple(raw))
 
 
 def unit_circle_pairs():

@@ -82,6 +82,34 @@ typedef struct gudni_shape_entry {
     float    left, top, right, bottom; /* shapeBox (includes control points)                  */
 } gudni_shape_entry;
 
+/* ---- level 3 inputs: raw outlines + transformer stacks (what the scene holds BEFORE serialisation) ----
+ * CurvePair — Figure/Outline.hs:55-57: an on-curve point and the control point towards the next one. */
+typedef struct gudni_curve_pair {
+    float on_x, on_y, off_x, off_y;
+} gudni_curve_pair;
+/* Outline — Figure/Outline.hs:59-61: a closed loop of curve pairs, `n_pairs` of them from `first_pair`.
+ * Outlines may be shared by any number of shapes (one unit circle, 100,000 placements). */
+typedef struct gudni_outline {
+    uint32_t first_pair, n_pairs;
+} gudni_outline;
+/* One simple transformation — Figure/Transformer.hs:94-105.  A rotation carries cos and sin of its angle
+ * (the caller's libm computes them, as the Haskell side would), so the library only multiplies. */
+enum { GUDNI_TRANSFORM_TRANSLATE = 0, GUDNI_TRANSFORM_SCALE = 1, GUDNI_TRANSFORM_ROTATE = 2 };
+typedef struct gudni_transform {
+    uint32_t kind;     /* GUDNI_TRANSFORM_*                                             */
+    float a, b;        /* translate: (dx, dy); scale: (factor, -); rotate: (cos, sin)   */
+    uint32_t reserved;
+} gudni_transform;
+/* A shape as the scene tree holds it (Raster/TraverseShapeTree.hs:35-80 hands onShape exactly this):
+ * tag, its outlines, and the transformer stack above it, listed outermost first — `tTranslate p .
+ * tScale s $ shape` is {translate p, scale s} — and applied last to first (CombineTransform, :105). */
+typedef struct gudni_outline_shape {
+    uint64_t tag;                          /* as gudni_shape_entry.tag */
+    uint32_t first_outline, n_outlines;    /* into outlines[]          */
+    uint32_t first_transform, n_transforms;/* into transforms[]        */
+    uint32_t reserved[2];
+} gudni_outline_shape;                     /* 32 bytes */
+
 /* Per-frame statistics — replaces the reference's putStrLn/`tr` logging. */
 typedef struct gudni_stats {
     int64_t n_tiles;            /* leaf tiles rendered                                        */
@@ -91,6 +119,8 @@ typedef struct gudni_stats {
     int64_t n_overflow_threads; /* column-threads that exceeded max_thresholds (UB in ref.)   */
     int64_t algorithmic_bytes;  /* A(frame), SURVEY.md §8(d)                                  */
     float   ms_upload, ms_bin, ms_raster, ms_download; /* CUDA-event stage times              */
+    float   ms_strands;          /* level 3 only: outlines -> geometry heap + shape entries */
+    float   reserved;
 } gudni_stats;
 
 typedef enum gudni_status {
@@ -186,6 +216,27 @@ int gudni_b200_frame_begin_device(gudni_ctx* ctx,
                                   const float background_rgba[4],
                                   int width, int height, int frame_number);
 int gudni_b200_raster_scene_device(gudni_ctx* ctx, const void* dev_entries, int n_entries);
+/* Level 3 — strand building behind the shim as well: replaces onShape's
+ * geometry work (Raster/Serialize.hs:148-177: applyTransformer, boxOf, excludeBox, appendGeoRef),
+ * enclose (Raster/Enclosure.hs:62-73), outlineToStrands (Raster/Strand.hs:153-178), replaceKnobs
+ * (Raster/Deknob.hs:104-108) and the reorder table (Raster/ReorderTable.hs:96-110), then continues as
+ * level 2.  Call frame_begin with no geometry (NULL, 0); shapes in scene order (first = top-most).
+ * Shapes whose transformed bounding box misses the canvas are dropped, as excludeBox drops them. */
+int gudni_b200_raster_outlines(gudni_ctx* ctx,
+                               const gudni_outline_shape* shapes, int n_shapes,
+                               const gudni_outline* outlines, int n_outlines,
+                               const gudni_curve_pair* pairs, int64_t n_pairs,
+                               const gudni_transform* transforms, int n_transforms);
+/* Same with the four arrays already on the device (bench.py's inputs-in-HBM leg; indices are trusted). */
+int gudni_b200_raster_outlines_device(gudni_ctx* ctx,
+                                      const void* dev_shapes, int n_shapes,
+                                      const void* dev_outlines, int n_outlines,
+                                      const void* dev_pairs, int64_t n_pairs,
+                                      const void* dev_transforms, int n_transforms);
+/* Debug: the geometry heap and shape entries level 3 built for the last frame (either may be NULL to
+ * query sizes). */
+int gudni_b200_debug_strands(gudni_ctx* ctx, void* geometry, size_t geometry_capacity, size_t* geometry_bytes,
+                             gudni_shape_entry* entries, int64_t entry_capacity, int64_t* n_entries);
 /* Optional: page-lock a caller-owned host buffer that stays at the same address across frames (a
  * Haskell `Pile`'s storage, the SDL texture) so the copies in frame_begin / raster_scene / frame_end run
  * as direct DMA instead of going through the driver's staging buffer.  Must be unregistered before the
