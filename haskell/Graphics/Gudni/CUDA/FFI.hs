@@ -5,6 +5,7 @@
 -- (src/Graphics/Gudni/Interface/GLInterop.hs:60-113).
 module Graphics.Gudni.CUDA.FFI where
 
+import Data.Int (Int64)
 import Foreign.C.Types
 import Foreign.C.String (CString)
 import Foreign.Ptr
@@ -38,6 +39,19 @@ foreign import ccall safe "gudni_b200_raster_job"
 
 foreign import ccall safe "gudni_b200_raster_scene"
   c_rasterScene :: Ptr GudniCtx -> Ptr () -> CInt -> IO CInt   -- un-binned shape entries (32 bytes each)
+
+-- | Level 3: the scene before serialisation.  Replaces onShape's geometry work (Raster/Serialize.hs:148-177),
+-- enclose (Raster/Enclosure.hs:62-73) and outlineToStrands (Raster/Strand.hs:153-178); call c_frameBegin
+-- with a null geometry pile.  Records: shape 32 bytes (tag, outline slice, transform slice), outline 8 bytes
+-- (pair slice), curve pair 16 bytes (onCurve, offCurve), transform 16 bytes (kind, a, b) — see
+-- include/gudni_b200.h.
+foreign import ccall safe "gudni_b200_raster_outlines"
+  c_rasterOutlines :: Ptr GudniCtx
+                   -> Ptr () -> CInt            -- shapes as traverseShapeTree visits them (first = top-most)
+                   -> Ptr () -> CInt            -- outlines (shared between shapes: one glyph, many placements)
+                   -> Ptr CFloat -> Int64       -- curve pairs
+                   -> Ptr () -> CInt            -- simple transformations, outermost first per shape
+                   -> IO CInt
 
 foreign import ccall safe "gudni_b200_frame_end"
   c_frameEnd :: Ptr GudniCtx -> Ptr CUInt {- HostBitmapTarget pointer, DrawTarget.hs:34 -} -> Ptr () -> IO CInt
