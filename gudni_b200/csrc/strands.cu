@@ -1,10 +1,12 @@
 // strands.cu — kernels and launcher of level 3 (strand_build.cuh has the per-shape logic and the
 // reference citations).  Three launches per frame:
 //   strand_measure_kernel  thread / shape: transformed bounding box, canvas culling, strand count,
-//                          16-byte units of geometry                      -> ShapeMeasure[] (24 B / shape)
-//   strand_scan_kernel     one CTA, tiles of 8,192 shapes: exclusive sums of (kept, units, strands)
-//                          -> entry index and geometry offset per shape, totals for the host
-//   strand_emit_kernel     thread / kept shape: gudni_shape_entry + the strands in tree order
+//                          16-byte units of geometry -> ShapeMeasure[] (24 B / shape), and per CTA of 256
+//                          shapes the sums of (kept, units, strands)
+//   strand_scan_kernel     one CTA: those per-CTA sums become exclusive prefixes; totals for the host
+//                          (a first version scanned all shapes in this one CTA: 185 us of the 304 on S4)
+//   strand_emit_kernel     thread / shape: CTA-local scan + the CTA's prefix give the entry index and the
+//                          heap offset; gudni_shape_entry + the strands in tree order
 // Bound: HBM in principle (S4: 6.4 MB in, 35 MB out); in this first version a thread writes its shape's
 // 288 bytes alone, so the stores are 32-byte sectors rather than full lines.
 #include "context.cuh"
@@ -15,102 +17,135 @@ namespace gudni_strands {
 
 __constant__ ReorderTable cTable;
 
-struct ScanOut {
-    uint32_t entryIndex;     // position among the kept shapes, or 0xFFFFFFFF if culled
-    uint32_t geoStart;       // 16-byte units
+constexpr int kBlock = 256;          // shapes per CTA in the measure and emit kernels
+
+struct BlockSums {                   // per CTA of the measure kernel; after the scan: exclusive prefixes
+    uint32_t kept, strands;
+    unsigned long long units;
 };
 
-__global__ void __launch_bounds__(256) strand_measure_kernel(const gudni_outline_shape* shapes, int nShapes,
-                                                             const gudni_outline* outlines, const gudni_curve_pair* pairs,
-                                                             const gudni_transform* transforms, int width, int height,
-                                                             ShapeMeasure* measures) {
+// exclusive scan of (kept, units) over the CTA's threads; totals in *sumKept / *sumUnits.  All threads call it.
+__device__ __forceinline__ void blockScan(uint32_t kept, unsigned long long units, uint32_t& exKept,
+                                          unsigned long long& exUnits, uint32_t* sumKept, unsigned long long* sumUnits) {
+    __shared__ uint32_t warpKept[32];
+    __shared__ unsigned long long warpUnits[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = (blockDim.x + 31) >> 5;
+    uint32_t incK = kept;
+    unsigned long long incU = units;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t k2 = __shfl_up_sync(0xFFFFFFFFu, incK, d);
+        const unsigned long long u2 = __shfl_up_sync(0xFFFFFFFFu, incU, d);
+        if (lane >= d) { incK += k2; incU += u2; }
+    }
+    __syncthreads();                                   // the arrays may still be read from a previous call
+    if (lane == 31) { warpKept[warp] = incK; warpUnits[warp] = incU; }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t wk = lane < nWarps ? warpKept[lane] : 0u;
+        unsigned long long wu = lane < nWarps ? warpUnits[lane] : 0ull;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t k2 = __shfl_up_sync(0xFFFFFFFFu, wk, d);
+            const unsigned long long u2 = __shfl_up_sync(0xFFFFFFFFu, wu, d);
+            if (lane >= d) { wk += k2; wu += u2; }
+        }
+        warpKept[lane] = wk;                           // inclusive over warps
+        warpUnits[lane] = wu;
+    }
+    __syncthreads();
+    exKept = (warp ? warpKept[warp - 1] : 0u) + (incK - kept);
+    exUnits = (warp ? warpUnits[warp - 1] : 0ull) + (incU - units);
+    if (sumKept) *sumKept = warpKept[nWarps - 1];
+    if (sumUnits) *sumUnits = warpUnits[nWarps - 1];
+}
+
+__global__ void __launch_bounds__(kBlock) strand_measure_kernel(const gudni_outline_shape* shapes, int nShapes,
+                                                                const gudni_outline* outlines, const gudni_curve_pair* pairs,
+                                                                const gudni_transform* transforms, int width, int height,
+                                                                ShapeMeasure* measures, BlockSums* blockSums) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nShapes) return;
-    ShapeMeasure m = measureShape(shapes[i], outlines, pairs, transforms);
-    if (culled(m, width, height)) m.units = 0xFFFFFFFFu;   // marks the shape as dropped
-    measures[i] = m;
+    uint32_t kept = 0u, strands = 0u;
+    unsigned long long units = 0ull;
+    if (i < nShapes) {
+        ShapeMeasure m = measureShape(shapes[i], outlines, pairs, transforms);
+        if (culled(m, width, height)) m.units = 0xFFFFFFFFu;   // marks the shape as dropped
+        else { kept = 1u; units = m.units; strands = m.strands; }
+        measures[i] = m;
+    }
+    uint32_t exK, sumK;
+    unsigned long long exU, sumU;
+    blockScan(kept, units, exK, exU, &sumK, &sumU);
+    // strands: only the CTA's total is needed
+    __shared__ uint32_t strandTotal;
+    if (threadIdx.x == 0) strandTotal = 0u;
+    __syncthreads();
+    for (int d = 16; d > 0; d >>= 1) strands += __shfl_down_sync(0xFFFFFFFFu, strands, d);
+    if ((threadIdx.x & 31) == 0 && strands) atomicAdd(&strandTotal, strands);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BlockSums b;
+        b.kept = sumK; b.strands = strandTotal; b.units = sumU;
+        blockSums[blockIdx.x] = b;
+    }
 }
 
 constexpr int kScanThreads = 1024;
-constexpr int kScanPerThread = 8;
 
+// One CTA: the per-CTA sums of the measure kernel become exclusive prefixes in place.
 // totals: [0] kept shapes, [1] geometry units, [2] strands
-__global__ void __launch_bounds__(kScanThreads) strand_scan_kernel(const ShapeMeasure* measures, int nShapes, ScanOut* out,
-                                                                   unsigned long long* totals) {
-    __shared__ unsigned long long warpKept[32], warpUnits[32];
+__global__ void __launch_bounds__(kScanThreads) strand_scan_kernel(BlockSums* blockSums, int nBlocks, unsigned long long* totals) {
     __shared__ unsigned long long carryKept, carryUnits, carryStrands;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carryKept = carryUnits = carryStrands = 0ull;
     unsigned long long strandsMine = 0ull;
     __syncthreads();
-    for (int base = 0; base < nShapes; base += kScanThreads * kScanPerThread) {
-        const int first = base + threadIdx.x * kScanPerThread;
-        uint32_t units[kScanPerThread];
-        unsigned long long kept = 0ull, sumUnits = 0ull;
-        for (int k = 0; k < kScanPerThread; k++) {
-            const int i = first + k;
-            units[k] = 0xFFFFFFFFu;
-            if (i < nShapes) {
-                units[k] = measures[i].units;
-                if (units[k] != 0xFFFFFFFFu) { kept++; sumUnits += units[k]; strandsMine += measures[i].strands; }
-            }
-        }
-        // exclusive scan of (kept, sumUnits) over the CTA: warp shuffle, then the warp totals
-        unsigned long long incK = kept, incU = sumUnits;
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long k2 = __shfl_up_sync(0xFFFFFFFFu, incK, d), u2 = __shfl_up_sync(0xFFFFFFFFu, incU, d);
-            if (lane >= d) { incK += k2; incU += u2; }
-        }
-        if (lane == 31) { warpKept[warp] = incK; warpUnits[warp] = incU; }
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long wk = warpKept[lane], wu = warpUnits[lane];
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long k2 = __shfl_up_sync(0xFFFFFFFFu, wk, d), u2 = __shfl_up_sync(0xFFFFFFFFu, wu, d);
-                if (lane >= d) { wk += k2; wu += u2; }
-            }
-            warpKept[lane] = wk;      // inclusive over warps
-            warpUnits[lane] = wu;
+    for (int base = 0; base < nBlocks; base += kScanThreads) {
+        const int b = base + threadIdx.x;
+        BlockSums in{0u, 0u, 0ull};
+        if (b < nBlocks) in = blockSums[b];
+        strandsMine += in.strands;
+        uint32_t exK, sumK;
+        unsigned long long exU, sumU;
+        blockScan(in.kept, in.units, exK, exU, &sumK, &sumU);
+        if (b < nBlocks) {
+            BlockSums out;
+            out.kept = (uint32_t)(carryKept + exK);
+            out.strands = in.strands;
+            out.units = carryUnits + exU;
+            blockSums[b] = out;
         }
         __syncthreads();
-        unsigned long long exK = carryKept + (warp ? warpKept[warp - 1] : 0ull) + (incK - kept);
-        unsigned long long exU = carryUnits + (warp ? warpUnits[warp - 1] : 0ull) + (incU - sumUnits);
-        for (int k = 0; k < kScanPerThread; k++) {
-            const int i = first + k;
-            if (i >= nShapes) break;
-            ScanOut o;
-            if (units[k] == 0xFFFFFFFFu) { o.entryIndex = 0xFFFFFFFFu; o.geoStart = 0u; }
-            else { o.entryIndex = (uint32_t)exK; o.geoStart = (uint32_t)exU; exK++; exU += units[k]; }
-            out[i] = o;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { carryKept += warpKept[31]; carryUnits += warpUnits[31]; }
+        if (threadIdx.x == 0) { carryKept += sumK; carryUnits += sumU; }
         __syncthreads();
     }
-    // strands: a plain CTA reduction
     for (int d = 16; d > 0; d >>= 1) strandsMine += __shfl_down_sync(0xFFFFFFFFu, strandsMine, d);
-    if (lane == 0) atomicAdd(&carryStrands, strandsMine);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&carryStrands, strandsMine);
     __syncthreads();
     if (threadIdx.x == 0) { totals[0] = carryKept; totals[1] = carryUnits; totals[2] = carryStrands; }
 }
 
-__global__ void __launch_bounds__(256) strand_emit_kernel(const gudni_outline_shape* shapes, int nShapes,
-                                                          const gudni_outline* outlines, const gudni_curve_pair* pairs,
-                                                          const gudni_transform* transforms, const ShapeMeasure* measures,
-                                                          const ScanOut* scan, uint8_t* geometry, gudni_shape_entry* entries) {
+__global__ void __launch_bounds__(kBlock) strand_emit_kernel(const gudni_outline_shape* shapes, int nShapes,
+                                                             const gudni_outline* outlines, const gudni_curve_pair* pairs,
+                                                             const gudni_transform* transforms, const ShapeMeasure* measures,
+                                                             const BlockSums* blockOffsets, uint8_t* geometry,
+                                                             gudni_shape_entry* entries) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nShapes) return;
-    const ScanOut so = scan[i];
-    if (so.entryIndex == 0xFFFFFFFFu) return;
+    ShapeMeasure m;
+    m.units = 0xFFFFFFFFu;
+    if (i < nShapes) m = measures[i];
+    const bool keep = m.units != 0xFFFFFFFFu;
+    uint32_t exK;
+    unsigned long long exU;
+    blockScan(keep ? 1u : 0u, keep ? (unsigned long long)m.units : 0ull, exK, exU, nullptr, nullptr);
+    if (!keep) return;
+    const BlockSums off = blockOffsets[blockIdx.x];
     const gudni_outline_shape s = shapes[i];
-    const ShapeMeasure m = measures[i];
+    const unsigned long long geoStart = off.units + exU;
     gudni_shape_entry e;
     e.tag = s.tag;
-    e.geo_start = so.geoStart;                    // appendGeoRef counts in 16-byte units, Serialize.hs:76-85
+    e.geo_start = (uint32_t)geoStart;             // appendGeoRef counts in 16-byte units, Serialize.hs:76-85
     e.num_strands = m.strands;
     e.left = m.left; e.top = m.top; e.right = m.right; e.bottom = m.bottom;
-    entries[so.entryIndex] = e;
-    emitShape(s, outlines, pairs, transforms, &cTable, geometry, 16ull * (uint64_t)so.geoStart);
+    entries[off.kept + exK] = e;
+    emitShape(s, outlines, pairs, transforms, &cTable, geometry, 16ull * geoStart);
 }
 
 }  // namespace gudni_strands
@@ -139,17 +174,16 @@ int buildStrands(gudni_ctx* ctx, const void* devShapes, int nShapes, const void*
     ctx->geometryPtr = ctx->geometry.ptr;
     if (nShapes == 0) return GUDNI_OK;
     GUDNI_TRY(devEnsure(ctx, ctx->strandMeasures, (size_t)nShapes * sizeof(ShapeMeasure)));
-    GUDNI_TRY(devEnsure(ctx, ctx->strandScan, (size_t)nShapes * sizeof(ScanOut) + 32));
+    const int blocks = (nShapes + kBlock - 1) / kBlock;
+    GUDNI_TRY(devEnsure(ctx, ctx->strandScan, (size_t)blocks * sizeof(BlockSums)));
     GUDNI_TRY(devEnsure(ctx, ctx->strandTotals, 32));
     GUDNI_TRY(devEnsure(ctx, ctx->entries, (size_t)nShapes * sizeof(gudni_shape_entry)));
-    const int blocks = (nShapes + 255) / 256;
-    strand_measure_kernel<<<blocks, 256, 0, ctx->stream>>>(
+    strand_measure_kernel<<<blocks, kBlock, 0, ctx->stream>>>(
         static_cast<const gudni_outline_shape*>(devShapes), nShapes, static_cast<const gudni_outline*>(devOutlines),
         static_cast<const gudni_curve_pair*>(devPairs), static_cast<const gudni_transform*>(devTransforms), ctx->width,
-        ctx->height, ctx->strandMeasures.as<ShapeMeasure>());
+        ctx->height, ctx->strandMeasures.as<ShapeMeasure>(), ctx->strandScan.as<BlockSums>());
     ctx->launches++;
-    strand_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>(ctx->strandMeasures.as<ShapeMeasure>(), nShapes,
-                                                            ctx->strandScan.as<ScanOut>(),
+    strand_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>(ctx->strandScan.as<BlockSums>(), blocks,
                                                             ctx->strandTotals.as<unsigned long long>());
     ctx->launches++;
     unsigned long long totals[3] = {0, 0, 0};
@@ -161,10 +195,10 @@ int buildStrands(gudni_ctx* ctx, const void* devShapes, int nShapes, const void*
     GUDNI_TRY(devEnsure(ctx, ctx->geometry, std::max<size_t>(geoBytes, 16)));
     if (totals[0]) {
         ctx->launches++;
-        strand_emit_kernel<<<blocks, 256, 0, ctx->stream>>>(
+        strand_emit_kernel<<<blocks, kBlock, 0, ctx->stream>>>(
             static_cast<const gudni_outline_shape*>(devShapes), nShapes, static_cast<const gudni_outline*>(devOutlines),
             static_cast<const gudni_curve_pair*>(devPairs), static_cast<const gudni_transform*>(devTransforms),
-            ctx->strandMeasures.as<ShapeMeasure>(), ctx->strandScan.as<ScanOut>(), ctx->geometry.as<uint8_t>(),
+            ctx->strandMeasures.as<ShapeMeasure>(), ctx->strandScan.as<BlockSums>(), ctx->geometry.as<uint8_t>(),
             ctx->entries.as<gudni_shape_entry>());
     }
     GUDNI_CUDA_TRY(ctx, cudaGetLastError());
