@@ -103,3 +103,76 @@ def test_pictures_glyphs_and_rectangles(lib):
 def test_s4_full_size(lib):
     """S4: 100,000 placements of one 16-pair outline -> 32 MB of geometry, 1.6 M Béziers."""
     assert_same_as_harness(lib, scenes.s4())
+
+
+def parse_heap(geometry, entries):
+    """Walk the geometry heap the way buildThresholdArray does (Kernels.cl:1557-1581): per shape
+    `num_strands` strands from 16*geo_start, each a u16 size in 8-byte units followed by size-1 points."""
+    out = []
+    for e in entries:
+        at = 16 * int(e["geo_start"])
+        strands = []
+        for _ in range(int(e["num_strands"])):
+            size = int(np.frombuffer(geometry[at:at + 2].tobytes(), "<u2")[0])
+            assert geometry[at + 2:at + 8].tobytes() == b"\0" * 6
+            pts = np.frombuffer(geometry[at + 8:at + 8 * size].tobytes(), "<f4").reshape(-1, 2)
+            strands.append(pts)
+            at += 8 * size
+        out.append(strands)
+    return out
+
+
+def test_rectangle_by_hand(lib):
+    """An axis-aligned w x h rectangle at (x,y), derived by hand from Raster/Strand.hs: the four sides are
+    four runs (vertical sides never join, Strand.hs:77-81); the run still open at the end — the left side —
+    comes first (:98-102); the bottom side runs right to left and is reversed (:137-143); a one-Bézier strand
+    is stored as [right end, left end, control] (ReorderTable.hs:96-104), controls at the midpoints
+    (Figure/Outline.hs:98-104)."""
+    from gudni_b200.scene import SceneBuilder
+    x, y, w, h = 3.25, 2.5, 7.0, 4.0
+    b = SceneBuilder(32, 32)
+    b.rectangle(b.solid(1, 0, 0, 1), w, h, [("translate", x, y)])
+    scene = b.freeze()
+    geometry, entries, n_strands = build(lib, scene)
+    assert n_strands == 4 and geometry.nbytes == 4 * 32
+    strands = parse_heap(geometry, entries)[0]
+    tl, tr, br, bl = (x, y), (x + w, y), (x + w, y + h), (x, y + h)
+    mid = lambda p, q: (0.5 * p[0] + 0.5 * q[0], 0.5 * p[1] + 0.5 * q[1])  # noqa: E731
+    expected = [
+        [tl, bl, mid(bl, tl)],       # left side, walked bottom-left -> top-left: [end, start, control]
+        [tr, tl, mid(tl, tr)],       # top side, left to right
+        [br, tr, mid(tr, br)],       # right side, top to bottom
+        [br, bl, mid(br, bl)],       # bottom side, walked right to left, stored left to right
+    ]
+    for got, want in zip(strands, expected):
+        assert np.array_equal(got, np.asarray(want, np.float32)), (got, want)
+    e = entries[0]
+    assert (e["left"], e["top"], e["right"], e["bottom"]) == (np.float32(x), np.float32(y), np.float32(x + w), np.float32(y + h))
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_structural_invariants(lib, case):
+    """What Kernels.cl relies on: size field = 2n+2 with 1 <= n <= 16, every strand runs
+    left to right and is x-monotone (so the tree search by x is valid), the tree order is a search tree: the
+    node at heap slot i splits the x-range of its subtree; strands tile the shape's slice of the heap."""
+    rng = np.random.default_rng(5000 + case)
+    scene = scenes.mixed_bag(int(rng.integers(20, 200)), int(rng.integers(50, 500)), int(rng.integers(50, 400)), 9000 + case)
+    geometry, entries, _ = build(lib, scene)
+    curves = 0
+    for strands in parse_heap(geometry, entries):
+        for pts in strands:
+            n = (len(pts) - 1) // 2
+            assert len(pts) == 2 * n + 1 and 1 <= n <= 16
+            curves += n
+            right, left = pts[0], pts[1]
+            assert left[0] <= right[0]
+            tree = pts[3::2][:n - 1] if n > 1 else np.zeros((0, 2), np.float32)    # on-curve points, heap order
+
+            def check(i, lo, hi):
+                if i >= len(tree):
+                    return
+                assert lo <= tree[i][0] <= hi, (i, lo, tree[i][0], hi)
+                check(2 * i + 1, lo, tree[i][0])
+                check(2 * i + 2, tree[i][0], hi)
+            check(0, left[0], right[0])
+    assert curves == scene.curves
