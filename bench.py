@@ -190,7 +190,7 @@ def level3_reading(r, scene, dscene, stream, flush, torch):
             "host_serialisation_ms_1_core": t_host * 1e3}
 
 
-def opencl_reference_on_this_gpu(workload, timeout_s=150):
+def opencl_reference_on_this_gpu(workload, timeout_s=90):
     """Side measurement, not an arm: the reference's Kernels.cl, verbatim, under the OpenCL runtime of the
     GPU box (NVIDIA OpenCL on the same B200), same scene, same raster jobs — oracle/refbuild/ocl_run.py in a
     child process with a time limit.  Needs oracle/_ref/ocl_program.bin (built where /root/reference
@@ -466,6 +466,9 @@ def run_native(args, rank, world, local_rank):
                        "strips": strips.rows if world > 1 else None,
                        "gather_order": gather_order},
             "mpixel_per_s": scene.width * scene.height * value / 1e6,
+            # SURVEY.md §8(d) secondary work units
+            "mthreshold_per_s": (stats.n_thresholds * value / 1e6) if stats is not None else None,
+            "staged_bytes": int(a_bytes + 2 * 20 * stats.n_thresholds) if stats is not None else None,
             "clocks": clocks,
             "e2e": {"value": 1.0 / float(t_e2e.item()), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
