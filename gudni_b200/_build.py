@@ -97,3 +97,24 @@ def build_strand_check(force=False, verbose=False):
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
     return LIB_STRAND_CHECK
+
+
+LIB_RASTER_EMU = os.path.join(REPO, "tests", "native", "libraster_emu.so")
+
+
+def build_raster_emu(force=False, verbose=False):
+    """tests/native/libraster_emu.so: the raster kernels' own sources compiled with g++ against a host
+    stand-in for the CUDA device language and run under a SIMT emulator — a test helper, see
+    tests/native/raster_emu.cpp."""
+    src = os.path.join(REPO, "tests", "native", "raster_emu.cpp")
+    deps = [src, os.path.join(REPO, "tests", "native", "emu", "cuda_runtime.h"),
+            os.path.join(REPO, "include", "gudni_b200.h")] + _sources(CSRC, (".cu", ".cuh"))
+    if not force and _newer(LIB_RASTER_EMU, deps):
+        return LIB_RASTER_EMU
+    cmd = [_host_cxx(), "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
+           "-I", os.path.join(REPO, "tests", "native", "emu"), "-I", os.path.join(REPO, "include"),
+           "-o", LIB_RASTER_EMU, src]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_RASTER_EMU

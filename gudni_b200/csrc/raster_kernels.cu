@@ -84,7 +84,11 @@ __global__ void __launch_bounds__(kGenWarpsPerCta * 32, GUDNI_GEN_MIN_CTAS) rast
 #define GUDNI_SWEEP_MIN_CTAS 1
 #endif
 __global__ void __launch_bounds__(kSweepWarpsPerCta * 32, GUDNI_SWEEP_MIN_CTAS) raster_sweep_kernel(const FrameParams P, int tileBase, int nTiles) {
+#ifdef GUDNI_HOST_EMULATION
+    unsigned char* smemRaw = cuemu::dynamicShared;
+#else
     extern __shared__ __align__(16) unsigned char smemRaw[];
+#endif
     WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smemRaw);
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -218,6 +222,7 @@ __global__ void selftest_div3_kernel(unsigned long long n, unsigned long long se
     if (bad) atomicAdd(mismatches, bad);
 }
 
+#ifndef GUDNI_HOST_EMULATION   // the emulator drives the kernels itself (tests/native/raster_emu.cpp)
 namespace gudni_launch {
 int strandBounds(gudni_ctx* ctx, const void* geometry, const void* records, int stride, int count, float2* bounds) {
     if (count <= 0) return GUDNI_OK;
@@ -276,3 +281,4 @@ int rasterSpill(gudni_ctx* ctx, const FrameParams& P) {
 }
 
 }  // namespace gudni_launch
+#endif  // GUDNI_HOST_EMULATION

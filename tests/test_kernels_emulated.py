@@ -1,0 +1,104 @@
+"""The CUDA kernels themselves in the CPU suite.
+
+tests/native/raster_emu.cpp compiles gudni_b200/csrc/raster_kernels.cu (+ raster_device.cuh, raster_warp.cuh —
+the text nvcc compiles, unchanged) with g++ against a host stand-in for the CUDA device language
+(tests/native/emu/cuda_runtime.h) and runs it under a cooperative SIMT emulator: one fiber per CUDA thread, warp
+shuffles / ballots / __syncthreads as rendezvous points, one CTA at a time, deadlock detection for collectives
+that cannot complete.  These tests hold the emulated kernels — generate, sweep with its colour cache and
+pending list, the HBM-queue replay of spilled threads, tile ordering, strand bounds — to the oracle: image,
+per-thread threshold counts and shape-bit counts, bit-exact.  It is not the product path (that needs a B200 and
+has no fallback) and not a performance model; it is how a kernel change is checked when no GPU is at hand."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from gudni_b200 import _build, scenes
+from gudni_b200.formats import CANONICAL_SPEC, CSpec, RasterSpec, SHAPE_DTYPE
+from oracle import oracle
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = ctypes.CDLL(_build.build_raster_emu())
+    c = ctypes
+    L.raster_emu_frame.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int,
+                                   c.POINTER(CSpec), c.c_void_p, c.c_int64, c.c_void_p, c.c_void_p, c.c_int, c.c_int64,
+                                   c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
+    return L
+
+
+def run(L, scene, spec=CANONICAL_SPEC):
+    """Level 1 of the ABI the way the shim lays a frame out: all jobs end to end."""
+    ref = oracle.render(scene, spec, taps=True)
+    assert ref.overflow_threads == 0
+    tiles, shapes, base = [], [], []
+    shape_base = column_base = 0
+    for job in ref.jobs:
+        t = job.tiles.copy()
+        t["shape_start"] += shape_base
+        base.append((column_base + job.tiles["column_allocation"]).astype(np.int32))
+        tiles.append(t)
+        shapes.append(job.shapes)
+        shape_base += len(job.shapes)
+        column_base += job.columns
+    tiles = np.ascontiguousarray(np.concatenate(tiles))
+    shapes = np.ascontiguousarray(np.concatenate(shapes)) if shape_base else np.zeros(1, SHAPE_DTYPE)
+    base = np.ascontiguousarray(np.concatenate(base))
+    out = np.zeros((scene.height, scene.width), np.uint32)
+    counts = np.zeros(column_base, np.int32)
+    bits = np.zeros(column_base, np.int32)
+    stats = np.zeros(4, np.int64)
+    g = np.ascontiguousarray(scene.geometry)
+    s = np.ascontiguousarray(scene.substances, np.float32)
+    p = np.ascontiguousarray(scene.picture_bytes)
+    u = np.ascontiguousarray(scene.picture_uses)
+    bg = np.ascontiguousarray(scene.background, np.float32)
+    ptr = lambda a: a.ctypes.data if a.size else None  # noqa: E731
+    cs = spec.to_c()
+    rc = L.raster_emu_frame(ptr(g), g.nbytes, ptr(s), ptr(p), ptr(u), bg.ctypes.data, scene.width, scene.height,
+                            ctypes.byref(cs), shapes.ctypes.data, shape_base, tiles.ctypes.data, base.ctypes.data,
+                            len(tiles), column_base, out.ctypes.data, counts.ctypes.data, bits.ctypes.data, stats.ctypes.data)
+    assert rc == 0
+    assert np.array_equal(counts, np.concatenate(ref.n_thresholds)), "per-thread threshold counts"
+    assert np.array_equal(bits, np.concatenate(ref.shape_bits)), "per-thread shape bits"
+    assert stats[0] == ref.total_thresholds and stats[2] == 0
+    bad = np.argwhere(out != ref.image)
+    assert len(bad) == 0, f"{len(bad)} pixels differ, first at (y,x)={bad[:5].tolist()}"
+    return stats
+
+
+CATALOGUE = [scenes.tiny_square, scenes.medium_square, scenes.full_rectangle, scenes.stack_of_squares,
+             scenes.open_square, scenes.concentric_squares2, scenes.concentric_squares3,
+             scenes.six_point_rectangle, scenes.hour_glass, scenes.translucent_stack]
+
+
+@pytest.mark.parametrize("make", CATALOGUE, ids=lambda f: f.__name__)
+def test_catalogue_scenes(emu, make):
+    run(emu, make())
+
+
+def test_circles_rectangles_pictures(emu):
+    run(emu, scenes.fuzzy_circles(150, 200, 150, 4, 40, 6))
+    run(emu, scenes.random_rectangles(120, 200, 160, 7))
+    run(emu, scenes.picture_scene(320, 300, flowers_size=(350, 200)))
+    run(emu, scenes.mixed_bag(120, 300, 200, 7003))
+
+
+def test_small_tile_spec(emu):
+    spec = RasterSpec(64, 64, 64, 256, 254, 127)
+    run(emu, scenes.fuzzy_circles(200, 150, 130, 5, 40, 0x1234), spec)
+
+
+def test_queue_leaves_the_shared_memory_window(emu):
+    stats = run(emu, scenes.thin_rectangles(60, width=64, spacing=3.0, thickness=1.3))
+    assert stats[1] == 0                      # > 64 thresholds per column, still on chip
+
+
+def test_replay_of_spilled_threads(emu):
+    """Queues past the on-chip capacity of 256, and tiles with more shapes than stack bits at the 8-pixel
+    floor: both go through the lane-private HBM-queue replay kernel."""
+    stats = run(emu, scenes.thin_rectangles(150, width=256, height=256, spacing=1.5, thickness=0.7, one_shape=True))
+    assert stats[1] > 0
+    stats = run(emu, scenes.fuzzy_circles(1200, 96, 96, 5, 50, 77))
+    assert stats[1] > 0
