@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(256) bin_emit(const BinParams P) {
 
 }  // namespace
 
+#ifndef GUDNI_HOST_EMULATION   // the emulator drives the kernels itself (tests/native/raster_emu.cpp)
 namespace gudni_bin {
 
 static int log2ceil(int x) { int d = 0; while ((1 << d) < x) d++; return d; }
@@ -478,3 +479,4 @@ int binScene(gudni_ctx* ctx, const gudni_shape_entry* devEntries, int n) {
 }
 
 }  // namespace gudni_bin
+#endif  // GUDNI_HOST_EMULATION

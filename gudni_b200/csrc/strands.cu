@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kBlock) strand_emit_kernel(const gudni_outline
 
 }  // namespace gudni_strands
 
+#ifndef GUDNI_HOST_EMULATION   // the emulator drives the kernels itself (tests/native/raster_emu.cpp)
 namespace gudni_launch {
 
 int strandTableInit(gudni_ctx* ctx) {
@@ -210,3 +211,4 @@ int buildStrands(gudni_ctx* ctx, const void* devShapes, int nShapes, const void*
 }
 
 }  // namespace gudni_launch
+#endif  // GUDNI_HOST_EMULATION

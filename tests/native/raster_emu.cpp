@@ -72,52 +72,56 @@ void runBlock(void (*entry)(void*), void* args, dim3 grid, dim3 block, uint3 bid
 }  // namespace cuemu
 
 #include "../../gudni_b200/csrc/raster_kernels.cu"
+#include "../../gudni_b200/csrc/binning.cu"
+#include "../../gudni_b200/csrc/strands.cu"
 
 #include <cstring>
 
 using namespace gudni_dev;
 
-extern "C" {
+namespace {
 
-// One frame at level 1 of the ABI: the jobs' shapes and tiles laid end to end as the shim lays them
-// (shape_start rebased, thread_base = first column-thread of each tile).  Returns 0; fills the image, the
-// per-thread taps (may be null) and stats[0..3] = thresholds, spilled threads, overflowed threads, switches.
-int raster_emu_frame(const void* geometry, size_t geometry_bytes, const float* substances, const uint8_t* picture_bytes,
-                     const gudni_picture_use* picture_uses, const float* background, int width, int height,
-                     const gudni_spec* spec, const gudni_shape* shapes, int64_t n_shapes, const gudni_tile* tiles,
-                     const int32_t* thread_base, int n_tiles, int64_t n_columns, uint32_t* out, int32_t* dbg_thresholds,
-                     int32_t* dbg_shape_bits, int64_t* stats) {
+struct FrameInputs {
+    const void* geometry; size_t geometryBytes;
+    const float* substances; const uint8_t* pictureBytes; const gudni_picture_use* pictureUses; const float* background;
+    int width, height; const gudni_spec* spec;
+};
+
+// rasterTiles + rasterSpill of raster_kernels.cu with host buffers and emulated launches
+void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShapes, const void* boundsRecords, int boundsStride,
+                 int64_t nBoundsRecords, const gudni_tile* tiles, const int32_t* threadBase, int nTiles, int64_t nColumns,
+                 uint32_t* out, int32_t* dbgThresholds, int32_t* dbgShapeBits, int64_t* stats) {
     FrameParams P{};
     int depth = 0;
-    while ((1 << depth) < spec->threads_per_tile) depth++;
+    while ((1 << depth) < in.spec->threads_per_tile) depth++;
     std::vector<unsigned long long> counters(kCountersBytes / 8 + 8, 0ull);
     const int spillCapacity = 1 << 16, spillSlots = 128;
     std::vector<unsigned long long> spillList(spillCapacity);
-    const size_t threads = (size_t)n_tiles * spec->threads_per_tile;
-    const size_t entries = std::max<size_t>({threads * 24, (size_t)width * height / 4, (size_t)1 << 16});
+    const size_t threads = (size_t)nTiles * in.spec->threads_per_tile;
+    const size_t entries = std::max<size_t>({threads * 24, (size_t)in.width * in.height / 4, (size_t)1 << 16});
     std::vector<float4> thrStore(entries);
     std::vector<uint32_t> hdrStore(entries);
     std::vector<ThreadRec> recs(std::max<size_t>(threads, 32));
-    std::vector<uint32_t> order(std::max(n_tiles, 1));
-    std::vector<float2> bounds(geometry_bytes / 16 + 2);
-    std::vector<float4> spillThr((size_t)spillSlots * spec->max_thresholds);
-    std::vector<uint32_t> spillHdr((size_t)spillSlots * spec->max_thresholds);
-    P.geometry = static_cast<const uint8_t*>(geometry);
+    std::vector<uint32_t> order(std::max(nTiles, 1));
+    std::vector<float2> bounds(in.geometryBytes / 16 + 2);
+    std::vector<float4> spillThr((size_t)spillSlots * in.spec->max_thresholds);
+    std::vector<uint32_t> spillHdr((size_t)spillSlots * in.spec->max_thresholds);
+    P.geometry = static_cast<const uint8_t*>(in.geometry);
     P.shapes = shapes;
     P.tiles = tiles;
-    P.tileThreadBase = thread_base;
-    P.substances = reinterpret_cast<const float4*>(substances);
-    P.pictureData = picture_bytes;
-    P.pictureUses = picture_uses;
+    P.tileThreadBase = threadBase;
+    P.substances = reinterpret_cast<const float4*>(in.substances);
+    P.pictureData = in.pictureBytes;
+    P.pictureUses = in.pictureUses;
     P.out = out;
-    P.background = make_float4(background[0], background[1], background[2], background[3]);
-    P.width = width; P.height = height;
-    P.rowBegin = 0; P.rowEnd = height; P.rowOrigin = 0;
+    P.background = make_float4(in.background[0], in.background[1], in.background[2], in.background[3]);
+    P.width = in.width; P.height = in.height;
+    P.rowBegin = 0; P.rowEnd = in.height; P.rowOrigin = 0;
     P.computeDepth = depth;
-    P.maxShape = spec->max_shapes;
-    P.maxThresholds = spec->max_thresholds;
-    P.dbgThresholds = dbg_thresholds;
-    P.dbgShapeBits = dbg_shape_bits;
+    P.maxShape = in.spec->max_shapes;
+    P.maxThresholds = in.spec->max_thresholds;
+    P.dbgThresholds = dbgThresholds;
+    P.dbgShapeBits = dbgShapeBits;
     P.counters = counters.data();
     P.spillList = spillList.data();
     P.spillCapacity = spillCapacity;
@@ -127,24 +131,164 @@ int raster_emu_frame(const void* geometry, size_t geometry_bytes, const float* s
     P.threadRecs = recs.data();
     P.strandBounds = bounds.data();
     P.tileOrder = order.data();
-    P.numStreams = std::max(1, std::min(3, n_tiles));
-    if (dbg_thresholds) for (int64_t i = 0; i < n_columns; i++) dbg_thresholds[i] = -1;
-    if (dbg_shape_bits) for (int64_t i = 0; i < n_columns; i++) dbg_shape_bits[i] = -1;
-    if (n_tiles > 0) {
-        if (n_shapes > 0)
-            cuemu::launch(strand_bounds_kernel, dim3((unsigned)((n_shapes + 255) / 256)), dim3(256), P.geometry,
-                          reinterpret_cast<const uint8_t*>(shapes), (int)sizeof(gudni_shape), (int)n_shapes, bounds.data());
-        cuemu::launch(tile_order_kernel, dim3(1), dim3(256), tiles, 0, n_tiles, order.data());
-        cuemu::launch(raster_generate_kernel, dim3(2), dim3(kGenWarpsPerCta * 32), P, 0, n_tiles);
-        cuemu::launch(raster_sweep_kernel, dim3(2), dim3(kSweepWarpsPerCta * 32), P, 0, n_tiles);
+    P.numStreams = std::max(1, std::min(3, nTiles));
+    if (dbgThresholds) for (int64_t i = 0; i < nColumns; i++) dbgThresholds[i] = -1;
+    if (dbgShapeBits) for (int64_t i = 0; i < nColumns; i++) dbgShapeBits[i] = -1;
+    if (nTiles > 0) {
+        if (nBoundsRecords > 0)
+            cuemu::launch(strand_bounds_kernel, dim3((unsigned)((nBoundsRecords + 255) / 256)), dim3(256), P.geometry,
+                          static_cast<const uint8_t*>(boundsRecords), boundsStride, (int)nBoundsRecords, bounds.data());
+        cuemu::launch(tile_order_kernel, dim3(1), dim3(256), tiles, 0, nTiles, order.data());
+        cuemu::launch(raster_generate_kernel, dim3(2), dim3(kGenWarpsPerCta * 32), P, 0, nTiles);
+        cuemu::launch(raster_sweep_kernel, dim3(2), dim3(kSweepWarpsPerCta * 32), P, 0, nTiles);
         cuemu::launch(raster_spill_kernel, dim3(1), dim3(spillSlots), P, spillThr.data(), spillHdr.data(), spillSlots);
     }
+    (void)nShapes;
     if (stats) {
         stats[0] = (int64_t)counters[kCntThresholds];
         stats[1] = (int64_t)counters[kCntSpilled];
         stats[2] = (int64_t)counters[kCntOverflow];
         stats[3] = (int64_t)cuemu::S.switches;
     }
+}
+
+int log2ceil(int x) { int d = 0; while ((1 << d) < x) d++; return d; }
+
+// binScene of binning.cu with host buffers and emulated launches
+struct Binned {
+    std::vector<gudni_tile> tiles;
+    std::vector<gudni_shape> shapes;
+    std::vector<int32_t> threadBase;
+    int64_t nColumns = 0;
+    bool overflow = false;
+};
+void binStage(const FrameInputs& in, const gudni_shape_entry* entries, int n, Binned& out) {
+    const int canvasDepth = log2ceil(std::max(in.width, in.height));
+    const int tileDepth = log2ceil(in.spec->max_tile_size);
+    BinParams P{};
+    P.entries = entries;
+    P.nEntries = n;
+    P.rootDepth = std::min(canvasDepth, tileDepth);
+    P.rootSize = 1 << P.rootDepth;
+    P.rootsPerSide = (1 << canvasDepth) / P.rootSize;
+    P.rowBegin = 0;
+    P.rowEnd = 1 << 30;
+    P.maxStrands = (uint32_t)in.spec->max_strands_per_tile;
+    const int cells = std::max(1, P.rootSize / kMinTile);
+    P.maxNodes = cells * cells;
+    P.maxLevels = 2 * std::max(0, P.rootDepth - 3) + 2;
+    P.threadsPerTile = in.spec->threads_per_tile;
+    P.tilesPerCall = in.spec->threads_per_tile;
+    P.columnsPerTile = in.spec->max_tiles_per_call;
+    const size_t nRoots = (size_t)P.rootsPerSide * P.rootsPerSide;
+    std::vector<uint32_t> w(nRoots * 8, 0u);
+    std::vector<BinNode> frontier(nRoots * 2 * (size_t)P.maxNodes);
+    std::vector<uint32_t> arena((size_t)32 * std::max(n, 1) + ((size_t)4 << 20));
+    std::vector<unsigned long long> counters(8, 0ull);
+    P.rootCount = w.data(); P.rootStrands = w.data() + nRoots; P.rootStart = w.data() + 2 * nRoots; P.rootCursor = w.data() + 3 * nRoots;
+    P.leafCount = w.data() + 4 * nRoots; P.refCount = w.data() + 5 * nRoots; P.tileOffset = w.data() + 6 * nRoots; P.shapeOffset = w.data() + 7 * nRoots;
+    P.frontier = frontier.data();
+    P.counters = counters.data();
+    P.arena = arena.data();
+    P.arenaCap = arena.size();
+    const int blocks = (n + 255) / 256;
+    if (n) cuemu::launch(bin_root_count, dim3(blocks), dim3(256), P);
+    cuemu::launch(bin_root_scan, dim3(1), dim3(1024), P);
+    if (n) cuemu::launch(bin_root_fill, dim3(blocks), dim3(256), P);
+    cuemu::launch(bin_subdivide, dim3((unsigned)nRoots), dim3(256), P);
+    cuemu::launch(bin_leaf_scan, dim3(1), dim3(1024), P);
+    out.overflow = counters[kOverflow] != 0 || counters[kTooManyShapes] != 0;
+    const int64_t nTiles = (int64_t)counters[kTotalTiles], nRefs = (int64_t)counters[kTotalRefs];
+    out.tiles.assign(std::max<int64_t>(nTiles, 1), gudni_tile{});
+    out.shapes.assign(nRefs + 1, gudni_shape{});
+    out.threadBase.assign(std::max<int64_t>(nTiles, 1), 0);
+    P.tiles = out.tiles.data();
+    P.shapes = out.shapes.data();
+    P.tileThreadBase = out.threadBase.data();
+    cuemu::launch(bin_emit, dim3((unsigned)nRoots), dim3(256), P);
+    out.tiles.resize(nTiles);
+    out.shapes.resize(nRefs);
+    out.threadBase.resize(nTiles);
+    out.nColumns = nTiles * (int64_t)P.columnsPerTile;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Level 1: the jobs' shapes and tiles laid end to end as the shim lays them (shape_start rebased,
+// thread_base = first column-thread of each tile).  stats[0..3] = thresholds, spilled threads, overflowed
+// threads, context switches.
+int raster_emu_frame(const void* geometry, size_t geometry_bytes, const float* substances, const uint8_t* picture_bytes,
+                     const gudni_picture_use* picture_uses, const float* background, int width, int height,
+                     const gudni_spec* spec, const gudni_shape* shapes, int64_t n_shapes, const gudni_tile* tiles,
+                     const int32_t* thread_base, int n_tiles, int64_t n_columns, uint32_t* out, int32_t* dbg_thresholds,
+                     int32_t* dbg_shape_bits, int64_t* stats) {
+    FrameInputs in{geometry, geometry_bytes, substances, picture_bytes, picture_uses, background, width, height, spec};
+    rasterStage(in, shapes, n_shapes, shapes, (int)sizeof(gudni_shape), n_shapes, tiles, thread_base, n_tiles, n_columns, out,
+                dbg_thresholds, dbg_shape_bits, stats);
+    return 0;
+}
+
+// Levels 2 and 3: tile binning (and, with `raw_shapes`, strand building) through the emulated kernels as well.
+// Level 2: `entries` + geometry given.  Level 3: raw outlines given, geometry/entries built and returned through
+// geometry_out / entries_out (capacities in bytes / records).  Binned tiles and shape lists come back through
+// tiles_out / shapes_out for comparison with the oracle's tile tree.  sizes[0..4] = entries, geometry bytes,
+// tiles, shape refs, columns.  Returns 0, or 1 if the binning scratch overflowed.
+int raster_emu_scene(const void* geometry, size_t geometry_bytes, const gudni_shape_entry* entries, int n_entries,
+                     const gudni_outline_shape* raw_shapes, int n_raw_shapes, const gudni_outline* outlines,
+                     const gudni_curve_pair* pairs, const gudni_transform* transforms,
+                     const float* substances, const uint8_t* picture_bytes, const gudni_picture_use* picture_uses,
+                     const float* background, int width, int height, const gudni_spec* spec, uint32_t* out,
+                     uint8_t* geometry_out, size_t geometry_capacity, gudni_shape_entry* entries_out, int64_t entry_capacity,
+                     gudni_tile* tiles_out, int64_t tile_capacity, gudni_shape* shapes_out, int64_t shape_capacity,
+                     int32_t* dbg_thresholds, int32_t* dbg_shape_bits, int64_t column_capacity, int64_t* sizes, int64_t* stats) {
+    std::vector<uint8_t> builtGeometry;
+    std::vector<gudni_shape_entry> builtEntries;
+    if (raw_shapes) {
+        using namespace gudni_strands;
+        buildReorderTable(cTable);
+        const int n = n_raw_shapes, blocks = (n + kBlock - 1) / kBlock;
+        std::vector<ShapeMeasure> measures(std::max(n, 1));
+        std::vector<BlockSums> sums(std::max(blocks, 1));
+        unsigned long long totals[3] = {0, 0, 0};
+        if (n) {
+            cuemu::launch(strand_measure_kernel, dim3(blocks), dim3(kBlock), raw_shapes, n, outlines, pairs, transforms, width,
+                          height, measures.data(), sums.data());
+            cuemu::launch(strand_scan_kernel, dim3(1), dim3(kScanThreads), sums.data(), blocks, totals);
+        }
+        builtGeometry.assign((size_t)totals[1] * 16 + 16, 0xCD);
+        builtEntries.assign(totals[0] + 1, gudni_shape_entry{});
+        if (totals[0])
+            cuemu::launch(strand_emit_kernel, dim3(blocks), dim3(kBlock), raw_shapes, n, outlines, pairs, transforms,
+                          (const ShapeMeasure*)measures.data(), (const BlockSums*)sums.data(), builtGeometry.data(),
+                          builtEntries.data());
+        builtGeometry.resize((size_t)totals[1] * 16);
+        builtEntries.resize(totals[0]);
+        geometry = builtGeometry.data();
+        geometry_bytes = builtGeometry.size();
+        entries = builtEntries.data();
+        n_entries = (int)builtEntries.size();
+        if (geometry_out && geometry_capacity >= geometry_bytes && geometry_bytes) memcpy(geometry_out, geometry, geometry_bytes);
+        if (entries_out && entry_capacity >= n_entries && n_entries) memcpy(entries_out, entries, (size_t)n_entries * sizeof(gudni_shape_entry));
+    }
+    static const uint8_t emptyGeometry[16] = {0};
+    static const gudni_shape_entry noEntry{};
+    if (!geometry) geometry = emptyGeometry;
+    if (!entries) entries = &noEntry;
+    FrameInputs in{geometry, geometry_bytes, substances, picture_bytes, picture_uses, background, width, height, spec};
+    Binned b;
+    binStage(in, entries, n_entries, b);
+    sizes[0] = n_entries; sizes[1] = (int64_t)geometry_bytes; sizes[2] = (int64_t)b.tiles.size();
+    sizes[3] = (int64_t)b.shapes.size(); sizes[4] = b.nColumns;
+    if (b.overflow) return 1;
+    if (tiles_out && tile_capacity >= (int64_t)b.tiles.size() && !b.tiles.empty()) memcpy(tiles_out, b.tiles.data(), b.tiles.size() * sizeof(gudni_tile));
+    if (shapes_out && shape_capacity >= (int64_t)b.shapes.size() && !b.shapes.empty()) memcpy(shapes_out, b.shapes.data(), b.shapes.size() * sizeof(gudni_shape));
+    const bool taps = dbg_thresholds && dbg_shape_bits && column_capacity >= b.nColumns;
+    static const gudni_shape noShape{};
+    rasterStage(in, b.shapes.empty() ? &noShape : b.shapes.data(), (int64_t)b.shapes.size(), entries, (int)sizeof(gudni_shape_entry),
+                n_entries, b.tiles.data(), b.threadBase.data(), (int)b.tiles.size(), b.nColumns, out,
+                taps ? dbg_thresholds : nullptr, taps ? dbg_shape_bits : nullptr, stats);
     return 0;
 }
 

@@ -102,3 +102,74 @@ def test_replay_of_spilled_threads(emu):
     assert stats[1] > 0
     stats = run(emu, scenes.fuzzy_circles(1200, 96, 96, 5, 50, 77))
     assert stats[1] > 0
+
+
+# ---- levels 2 and 3: the binning and strand-building kernels under the emulator as well ----------------------
+from gudni_b200.formats import ENTRY_DTYPE, TILE_DTYPE  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu_scene(emu):
+    c = ctypes
+    vp, i32, i64, sz = c.c_void_p, c.c_int, c.c_int64, c.c_size_t
+    emu.raster_emu_scene.argtypes = [vp, sz, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, c.POINTER(CSpec), vp,
+                                     vp, sz, vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, vp]
+    return emu
+
+
+def run_scene(L, scene, level, spec=CANONICAL_SPEC):
+    ref = oracle.render(scene, spec, taps=True)
+    ref_tiles, ref_shapes = oracle.tiles_in_tree_order(ref.jobs)
+    ptr = lambda a: a.ctypes.data if a is not None and a.size else None  # noqa: E731
+    g = np.ascontiguousarray(scene.geometry)
+    e = np.ascontiguousarray(scene.entries)
+    s = np.ascontiguousarray(scene.substances, np.float32)
+    p = np.ascontiguousarray(scene.picture_bytes)
+    u = np.ascontiguousarray(scene.picture_uses)
+    bg = np.ascontiguousarray(scene.background, np.float32)
+    raw = [np.ascontiguousarray(a) for a in scene.raw] if level == 3 else [None] * 4
+    out = np.zeros((scene.height, scene.width), np.uint32)
+    geometry_out = np.zeros(g.nbytes + 64, np.uint8)
+    entries_out = np.zeros(len(e) + 4, ENTRY_DTYPE)
+    tiles_out = np.zeros(len(ref_tiles) + 16, TILE_DTYPE)
+    shapes_out = np.zeros(len(ref_shapes) + 16, SHAPE_DTYPE)
+    columns = sum(j.columns for j in ref.jobs)
+    counts = np.zeros(columns, np.int32)
+    bits = np.zeros(columns, np.int32)
+    sizes = np.zeros(5, np.int64)
+    stats = np.zeros(4, np.int64)
+    cs = spec.to_c()
+    rc = L.raster_emu_scene(ptr(g) if level == 2 else None, g.nbytes if level == 2 else 0, ptr(e) if level == 2 else None,
+                            len(e) if level == 2 else 0, ptr(raw[0]), len(raw[0]) if level == 3 else 0, ptr(raw[1]), ptr(raw[2]),
+                            ptr(raw[3]), ptr(s), ptr(p), ptr(u), bg.ctypes.data, scene.width, scene.height, ctypes.byref(cs),
+                            out.ctypes.data, geometry_out.ctypes.data, geometry_out.nbytes, entries_out.ctypes.data,
+                            len(entries_out), tiles_out.ctypes.data, len(tiles_out), shapes_out.ctypes.data, len(shapes_out),
+                            counts.ctypes.data, bits.ctypes.data, columns, sizes.ctypes.data, stats.ctypes.data)
+    assert rc == 0
+    if level == 3:      # strands: heap and entries as the harness serialises them
+        assert sizes[0] == len(e) and sizes[1] == g.nbytes
+        assert entries_out[:len(e)].tobytes() == e.tobytes()
+        assert geometry_out[:g.nbytes].tobytes() == g.tobytes()
+    # binning: tiles in tree order, per-tile shape lists, column numbering
+    assert sizes[2] == len(ref_tiles) and sizes[3] == len(ref_shapes) and sizes[4] == columns
+    tiles = tiles_out[:len(ref_tiles)]
+    for field in ("left", "top", "right", "bottom", "h_depth", "v_depth", "shape_start", "shape_count"):
+        assert np.array_equal(tiles[field], ref_tiles[field]), field
+    assert shapes_out[:len(ref_shapes)].tobytes() == ref_shapes.tobytes()
+    # raster
+    assert np.array_equal(counts, np.concatenate(list(reversed(ref.n_thresholds))))
+    assert np.array_equal(bits, np.concatenate(list(reversed(ref.shape_bits))))
+    assert stats[0] == ref.total_thresholds
+    assert np.array_equal(out, ref.image)
+
+
+@pytest.mark.parametrize("level", [2, 3])
+def test_binning_and_strand_kernels(emu_scene, level):
+    run_scene(emu_scene, scenes.tiny_square(), level)
+    run_scene(emu_scene, scenes.fuzzy_circles(150, 200, 150, 4, 40, 6), level)
+    run_scene(emu_scene, scenes.mixed_bag(100, 300, 200, 7003), level)
+    run_scene(emu_scene, scenes.fuzzy_circles(400, 150, 130, 5, 40, 0x1234), level, RasterSpec(64, 64, 64, 256, 254, 127))
+
+
+def test_binning_splits_down_to_the_floor(emu_scene):
+    run_scene(emu_scene, scenes.fuzzy_circles(1200, 96, 96, 5, 50, 77), 2)
