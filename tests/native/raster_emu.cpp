@@ -79,6 +79,7 @@ void runBlock(void (*entry)(void*), void* args, dim3 grid, dim3 block, uint3 bid
 
 using namespace gudni_dev;
 
+static size_t g_storeEntriesOverride;
 namespace {
 
 struct FrameInputs {
@@ -98,7 +99,8 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
     const int spillCapacity = 1 << 16, spillSlots = 128;
     std::vector<unsigned long long> spillList(spillCapacity);
     const size_t threads = (size_t)nTiles * in.spec->threads_per_tile;
-    const size_t entries = std::max<size_t>({threads * 24, (size_t)in.width * in.height / 4, (size_t)1 << 16});
+    const size_t entries = g_storeEntriesOverride ? g_storeEntriesOverride
+                                                  : std::max<size_t>({threads * 24, (size_t)in.width * in.height / 4, (size_t)1 << 16});
     std::vector<float4> thrStore(entries);
     std::vector<uint32_t> hdrStore(entries);
     std::vector<ThreadRec> recs(std::max<size_t>(threads, 32));
@@ -151,6 +153,10 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
         stats[3] = (int64_t)cuemu::S.switches;
     }
 }
+
+}  // namespace
+// (g_storeEntriesOverride, declared above: raster_emu_set_store_entries forces the threshold store to run out)
+namespace {
 
 int log2ceil(int x) { int d = 0; while ((1 << d) < x) d++; return d; }
 
@@ -215,6 +221,10 @@ void binStage(const FrameInputs& in, const gudni_shape_entry* entries, int n, Bi
 }  // namespace
 
 extern "C" {
+
+// 0 restores the shim's sizing rule.  A store that is too small makes the generate kernel hand whole warps to
+// the replay kernel (raster_warp.cuh generateWarp): slow, not wrong.
+void raster_emu_set_store_entries(size_t n) { g_storeEntriesOverride = n; }
 
 // Level 1: the jobs' shapes and tiles laid end to end as the shim lays them (shape_start rebased,
 // thread_base = first column-thread of each tile).  stats[0..3] = thresholds, spilled threads, overflowed

@@ -173,3 +173,32 @@ def test_binning_and_strand_kernels(emu_scene, level):
 
 def test_binning_splits_down_to_the_floor(emu_scene):
     run_scene(emu_scene, scenes.fuzzy_circles(1200, 96, 96, 5, 50, 77), 2)
+
+
+def test_threshold_store_exhausted(emu):
+    """A hand-over store that is too small (the shim sizes it from the previous frame's demand, so a first
+    frame can meet this): the generate kernel gives whole warps to the replay kernel — slower, same pixels."""
+    emu.raster_emu_set_store_entries.argtypes = [ctypes.c_size_t]
+    emu.raster_emu_set_store_entries(600)
+    try:
+        stats = run(emu, scenes.fuzzy_circles(150, 200, 150, 4, 40, 6))
+        assert stats[1] > 0
+    finally:
+        emu.raster_emu_set_store_entries(0)
+
+
+def test_degenerate_outlines(emu_scene):
+    """Outlines of fewer than two curve pairs produce no strands (Strand.hs:175-177) but still count towards
+    the shape's bounding box (onShape boxes the outlines first); a shape made only of such outlines is an entry
+    without geometry."""
+    from gudni_b200.scene import SceneBuilder
+    b = SceneBuilder(64, 48, (0.1, 0.2, 0.3, 1.0))
+    red = b.solid(1, 0, 0, 0.5)
+    square = np.array([[10, 10, 20, 10], [30, 10, 30, 20], [30, 30, 20, 30], [10, 30, 10, 20]], np.float32)
+    b.shape(red, [square, np.array([[50, 40, 51, 41]], np.float32)])        # a real outline + a single pair
+    b.shape(b.solid(0, 1, 0, 1), [np.array([[5, 5, 6, 6]], np.float32)])    # only a single pair
+    scene = b.freeze()
+    assert scene.n_shapes == 2 and scene.entries["num_strands"][1] == 0
+    assert scene.entries["right"][0] == np.float32(51.0)
+    run_scene(emu_scene, scene, 3)
+    run_scene(emu_scene, scene, 2)

@@ -176,3 +176,16 @@ def test_structural_invariants(lib, case):
                 check(2 * i + 2, tree[i][0], hi)
             check(0, left[0], right[0])
     assert curves == scene.curves
+
+
+def test_degenerate_outlines(lib):
+    """Fewer than two curve pairs: no strands (Strand.hs:175-177), but the points still count towards the box."""
+    from gudni_b200.scene import SceneBuilder
+    b = SceneBuilder(64, 48)
+    square = np.array([[10, 10, 20, 10], [30, 10, 30, 20], [30, 30, 20, 30], [10, 30, 10, 20]], np.float32)
+    b.shape(b.solid(1, 0, 0, 0.5), [square, np.array([[50, 40, 51, 41]], np.float32)])
+    b.shape(b.solid(0, 1, 0, 1), [np.array([[5, 5, 6, 6]], np.float32)])
+    b.shape(b.solid(0, 0, 1, 1), [np.array([[500, 5, 600, 6]], np.float32)])      # off canvas: culled
+    scene = b.freeze()
+    assert scene.n_shapes == 2 and scene.culled == 1
+    assert_same_as_harness(lib, scene)
