@@ -5,6 +5,7 @@ levels 2 and 3).  Global and shared memory are host heap / static arrays there, 
 misaligned vector load in a kernel is reported like any host bug.
 
     python tools/emu_sanitize.py ubsan|asan
+    python tools/emu_sanitize.py coverage      # gcov line / branch coverage of the kernel sources by those scenarios
 """
 import ctypes
 import os
@@ -40,10 +41,33 @@ def scenario(lib_path):
     print("sanitized run complete: no reports")
 
 
+def coverage():
+    import shutil
+    work = "/tmp/gudni_emu_cov"
+    shutil.rmtree(work, ignore_errors=True)
+    os.makedirs(work)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    lib = os.path.join(work, "libraster_emu_cov.so")
+    subprocess.run([cxx, "-O0", "-g", "--coverage", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
+                    "-I", os.path.join(ROOT, "tests", "native", "emu"), "-I", os.path.join(ROOT, "include"), "-o", lib,
+                    os.path.join(ROOT, "tests", "native", "raster_emu.cpp")], check=True, cwd=work)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--run", lib], check=True, cwd=work)
+    out = subprocess.run(["gcov", "-b", "libraster_emu_cov.so-raster_emu.gcda"], cwd=work, capture_output=True, text=True).stdout
+    keep = False
+    for line in out.splitlines():
+        if line.startswith("File "):
+            keep = "/gudni_b200/csrc/" in line
+        if keep and (line.startswith("File ") or line.startswith("Lines executed") or line.startswith("Taken at least once")):
+            print(line)
+    print("annotated sources:", work, "(*.gcov)")
+
+
 def main():
     if len(sys.argv) == 3 and sys.argv[1] == "--run":
         return scenario(sys.argv[2])
     mode = sys.argv[1] if len(sys.argv) > 1 else "ubsan"
+    if mode == "coverage":
+        return coverage()
     flags, runtime, env = MODES[mode]
     lib = f"/tmp/libraster_emu_{mode}.so"
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
