@@ -126,7 +126,7 @@ def oracle_frame_sampler(scene, budget_s=12.0, kind=None):
     stride = max(1, int(np.ceil(est / budget_s)))
     picked = jobs[stride // 2::stride] if stride > 1 else jobs
     desc = (f"tile tree for the whole scene + {len(picked)} of {len(jobs)} raster jobs "
-            f"(every {stride}th job of {scene.name}), raster time scaled by {len(jobs)}/{len(picked)}"
+            f"(one job in {stride} of {scene.name}), raster time scaled by {len(jobs)}/{len(picked)}"
             if stride > 1 else f"one full frame of {scene.name} (tile tree + {len(jobs)} raster jobs)")
 
     def run():
