@@ -467,8 +467,8 @@ def run_native(args, rank, world, local_rank):
                        "gather_order": gather_order},
             "mpixel_per_s": scene.width * scene.height * value / 1e6,
             # SURVEY.md §8(d) secondary work units
-            "mthreshold_per_s": (stats.n_thresholds * value / 1e6) if stats is not None else None,
-            "staged_bytes": int(a_bytes + 2 * 20 * stats.n_thresholds) if stats is not None else None,
+            "mthreshold_per_s": (stats.n_thresholds * value / 1e6) if (stats is not None and world == 1) else None,
+            "staged_bytes": int(a_bytes + 2 * 20 * stats.n_thresholds) if (stats is not None and world == 1) else None,
             "clocks": clocks,
             "e2e": {"value": 1.0 / float(t_e2e.item()), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
