@@ -80,6 +80,7 @@ void runBlock(void (*entry)(void*), void* args, dim3 grid, dim3 block, uint3 bid
 using namespace gudni_dev;
 
 static size_t g_storeEntriesOverride;
+static int g_rowBegin = 0, g_rowEnd = 0;    // raster_emu_set_strip: rows of the canvas this "context" renders (0,0 = all)
 namespace {
 
 struct FrameInputs {
@@ -118,7 +119,9 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
     P.out = out;
     P.background = make_float4(in.background[0], in.background[1], in.background[2], in.background[3]);
     P.width = in.width; P.height = in.height;
-    P.rowBegin = 0; P.rowEnd = in.height; P.rowOrigin = 0;
+    P.rowBegin = g_rowEnd ? g_rowBegin : 0;
+    P.rowEnd = g_rowEnd ? g_rowEnd : in.height;
+    P.rowOrigin = 0;                                   // `out` is the whole canvas here
     P.computeDepth = depth;
     P.maxShape = in.spec->max_shapes;
     P.maxThresholds = in.spec->max_thresholds;
@@ -177,8 +180,10 @@ void binStage(const FrameInputs& in, const gudni_shape_entry* entries, int n, Bi
     P.rootDepth = std::min(canvasDepth, tileDepth);
     P.rootSize = 1 << P.rootDepth;
     P.rootsPerSide = (1 << canvasDepth) / P.rootSize;
-    P.rowBegin = 0;
-    P.rowEnd = 1 << 30;
+    // as binScene: the tile tree covers the power-of-two square around the canvas; root tiles below the last
+    // canvas row belong to the last strip
+    P.rowBegin = g_rowEnd ? g_rowBegin : 0;
+    P.rowEnd = (!g_rowEnd || g_rowEnd >= in.height) ? (1 << 30) : g_rowEnd;
     P.maxStrands = (uint32_t)in.spec->max_strands_per_tile;
     const int cells = std::max(1, P.rootSize / kMinTile);
     P.maxNodes = cells * cells;
@@ -225,6 +230,9 @@ extern "C" {
 // 0 restores the shim's sizing rule.  A store that is too small makes the generate kernel hand whole warps to
 // the replay kernel (raster_warp.cuh generateWarp): slow, not wrong.
 void raster_emu_set_store_entries(size_t n) { g_storeEntriesOverride = n; }
+
+// gudni_b200_frame_strip: whole root-tile rows [row_begin, row_end) of the canvas; (0, 0) restores the whole frame.
+void raster_emu_set_strip(int row_begin, int row_end) { g_rowBegin = row_begin; g_rowEnd = row_end; }
 
 // Level 1: the jobs' shapes and tiles laid end to end as the shim lays them (shape_start rebased,
 // thread_base = first column-thread of each tile).  stats[0..3] = thresholds, spilled threads, overflowed

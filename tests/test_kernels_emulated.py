@@ -202,3 +202,37 @@ def test_degenerate_outlines(emu_scene):
     assert scene.entries["right"][0] == np.float32(51.0)
     run_scene(emu_scene, scene, 3)
     run_scene(emu_scene, scene, 2)
+
+
+def test_strips_reassemble_the_frame(emu_scene):
+    """gudni_b200_frame_strip on the kernels' side: the binning kernels skip root tiles outside the strip, the
+    raster kernels' threads outside it are inactive.  Three strips of whole root-tile rows (64-pixel tiles)
+    rendered separately into one canvas give the frame, all entries passed to every strip."""
+    L = emu_scene
+    spec = RasterSpec(64, 64, 64, 256, 254, 127)
+    scene = scenes.fuzzy_circles(300, 200, 230, 5, 40, 0x57A1)
+    ref = oracle.render(scene, spec, taps=False)
+    ptr = lambda a: a.ctypes.data if a.size else None  # noqa: E731
+    g = np.ascontiguousarray(scene.geometry)
+    e = np.ascontiguousarray(scene.entries)
+    s = np.ascontiguousarray(scene.substances, np.float32)
+    bg = np.ascontiguousarray(scene.background, np.float32)
+    canvas = np.full((scene.height, scene.width), 0xDEADBEEF, np.uint32)
+    sizes, stats = np.zeros(5, np.int64), np.zeros(4, np.int64)
+    cs = spec.to_c()
+    total = 0
+    L.raster_emu_set_strip.argtypes = [ctypes.c_int, ctypes.c_int]
+    try:
+        for rows in ((0, 64), (64, 192), (192, 230)):
+            L.raster_emu_set_strip(*rows)
+            rc = L.raster_emu_scene(ptr(g), g.nbytes, ptr(e), len(e), None, 0, None, None, None, ptr(s), None, None,
+                                    bg.ctypes.data, scene.width, scene.height, ctypes.byref(cs), canvas.ctypes.data,
+                                    None, 0, None, 0, None, 0, None, 0, None, None, 0, sizes.ctypes.data, stats.ctypes.data)
+            assert rc == 0
+            total += int(stats[0])
+            # rows of the other strips are untouched so far or already final
+            assert np.array_equal(canvas[rows[0]:rows[1]], ref.image[rows[0]:rows[1]])
+    finally:
+        L.raster_emu_set_strip(0, 0)
+    assert np.array_equal(canvas, ref.image)
+    assert total == ref.total_thresholds
