@@ -8,7 +8,6 @@ timed from the library's own events (bin + raster ms, best and mean of `frames`)
 against the golden vector of the reference's kernels under OpenCL on a B200
 (tests/golden/opencl_b200_hashes.json) — a variant that is fast and wrong is marked WRONG, not ranked.
 Results go to stdout and gpurun_out/ab_variants.json."""
-import ctypes
 import glob
 import hashlib
 import json
