@@ -178,6 +178,16 @@ inline void syncthreads() {
     S.progress = true;
 }
 
+// rcp.approx.ftz.f32: the hardware's reciprocal is within about 1 ulp of 1/d; `rcpUlpError` moves the model's
+// answer that many ulps off the correctly rounded one, so tests can show that div3 (raster_device.cuh) does not
+// depend on which approximation it starts from.
+extern int rcpUlpError;
+inline float rcpApprox(float d) {
+    float r = (float)(1.0 / (double)d);
+    for (int i = 0; i < (rcpUlpError < 0 ? -rcpUlpError : rcpUlpError); i++) r = nextafterf(r, rcpUlpError < 0 ? 0.0f : INFINITY);
+    return r;
+}
+
 template <class T> inline uint64_t pack(T v) { uint64_t u = 0; static_assert(sizeof(T) <= 8, "shuffle operand"); memcpy(&u, &v, sizeof(T)); return u; }
 template <class T> inline T unpack(uint64_t u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
 

@@ -5,13 +5,13 @@
 // only) and it is not a performance model; what it gives is the kernels' logic — queues, warp-cooperative
 // sweep, colour cache, spill replay — checked against the oracle in the CPU test suite, deadlock detection for
 // mismatched collectives, and a way to try a kernel change before a GPU is at hand.
-// Division uses the plain IEEE `/` (-DGUDNI_NO_DIV3: div3 is bit-identical to it by construction and checked
-// on the device by gudni_b200_debug_selftest).  Not product, not oracle.
+// The shared-reciprocal division (div3) runs as on the device, from a model of rcp.approx whose error the tests
+// can set (raster_emu_set_rcp_error).  Not product, not oracle.
 #define GUDNI_HOST_EMULATION 1
-#define GUDNI_NO_DIV3 1
 #include <cuda_runtime.h>   // emu/cuda_runtime.h
 
 namespace cuemu {
+int rcpUlpError = 0;
 State S;
 unsigned char dynamicShared[228 * 1024];
 static void (*g_entry)(void*);
@@ -230,6 +230,39 @@ extern "C" {
 // 0 restores the shim's sizing rule.  A store that is too small makes the generate kernel hand whole warps to
 // the replay kernel (raster_warp.cuh generateWarp): slow, not wrong.
 void raster_emu_set_store_entries(size_t n) { g_storeEntriesOverride = n; }
+
+// ulps by which the modelled rcp.approx misses the correctly rounded reciprocal (0, +-1, +-2 ...)
+void raster_emu_set_rcp_error(int ulps) { cuemu::rcpUlpError = ulps; }
+
+// div3<true> (raster_device.cuh) against the host's IEEE division on n pseudo-random operand sets, the same
+// generator as the device's selftest_div3_kernel; returns the number of differing quotients.
+uint64_t raster_emu_selftest_div3(uint64_t n, uint64_t seed) {
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        unsigned long long z = seed + i * 0x9E3779B97F4A7C15ull;
+        float v[4];
+        for (int k = 0; k < 4; k++) {
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            const unsigned mode = (unsigned)(z >> 60);
+            float f = (float)((z >> 20) & 0xFFFFFFull) * (1.0f / 16777216.0f);
+            if (mode == 0) f = __uint_as_float((unsigned)(z >> 8) & 0x7FFFFFFFu);
+            else if (mode == 1) f = f * 0x1p-58f;
+            else if (mode == 2) f = 0.0f;
+            else if (mode == 3) f = 1.0f;
+            v[k] = f;
+        }
+        const float d = v[3];
+        if (!(d > 0.0f) || v[0] != v[0] || v[1] != v[1] || v[2] != v[2] || d != d) continue;
+        float qx, qy, qz;
+        div3<true>(v[0], v[1], v[2], d, qx, qy, qz);
+        const volatile float rx = v[0] / d, ry = v[1] / d, rz = v[2] / d;
+        bad += (__float_as_uint(qx) != __float_as_uint(rx)) + (__float_as_uint(qy) != __float_as_uint(ry)) +
+               (__float_as_uint(qz) != __float_as_uint(rz));
+    }
+    return bad;
+}
 
 // gudni_b200_frame_strip: whole root-tile rows [row_begin, row_end) of the canvas; (0, 0) restores the whole frame.
 void raster_emu_set_strip(int row_begin, int row_end) { g_rowBegin = row_begin; g_rowEnd = row_end; }

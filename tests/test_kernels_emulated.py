@@ -236,3 +236,22 @@ def test_strips_reassemble_the_frame(emu_scene):
         L.raster_emu_set_strip(0, 0)
     assert np.array_equal(canvas, ref.image)
     assert total == ref.total_thresholds
+
+
+def test_shared_reciprocal_division(emu):
+    """div3 (raster_device.cuh) — one reciprocal, a Newton step and FMA corrections for the three quotients of
+    `composite` — runs here from a model of rcp.approx.  It returns the correctly rounded quotient whichever
+    way the approximation errs (0, +-1, +-2, +-8 ulps), on the operand generator of the device's own self-test;
+    and a frame rendered with a reciprocal that is off by an ulp either way is the same frame."""
+    emu.raster_emu_selftest_div3.restype = ctypes.c_uint64
+    emu.raster_emu_selftest_div3.argtypes = [ctypes.c_uint64, ctypes.c_uint64]
+    emu.raster_emu_set_rcp_error.argtypes = [ctypes.c_int]
+    try:
+        for ulps in (0, 1, -1, 2, -2, 8, -8):
+            emu.raster_emu_set_rcp_error(ulps)
+            assert emu.raster_emu_selftest_div3(400_000, 1 + abs(ulps)) == 0, ulps
+        for ulps in (1, -1):
+            emu.raster_emu_set_rcp_error(ulps)
+            run(emu, scenes.fuzzy_circles(120, 160, 120, 4, 40, 9))
+    finally:
+        emu.raster_emu_set_rcp_error(0)
