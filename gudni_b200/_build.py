@@ -102,19 +102,20 @@ def build_strand_check(force=False, verbose=False):
 LIB_RASTER_EMU = os.path.join(REPO, "tests", "native", "libraster_emu.so")
 
 
-def build_raster_emu(force=False, verbose=False):
+def build_raster_emu(force=False, verbose=False, extra=(), suffix=""):
     """tests/native/libraster_emu.so: the raster kernels' own sources compiled with g++ against a host
     stand-in for the CUDA device language and run under a SIMT emulator — a test helper, see
     tests/native/raster_emu.cpp."""
     src = os.path.join(REPO, "tests", "native", "raster_emu.cpp")
     deps = [src, os.path.join(REPO, "tests", "native", "emu", "cuda_runtime.h"),
             os.path.join(REPO, "include", "gudni_b200.h")] + _sources(CSRC, (".cu", ".cuh"))
-    if not force and _newer(LIB_RASTER_EMU, deps):
-        return LIB_RASTER_EMU
-    cmd = [_host_cxx(), "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
-           "-I", os.path.join(REPO, "tests", "native", "emu"), "-I", os.path.join(REPO, "include"),
-           "-o", LIB_RASTER_EMU, src]
+    # `extra` / `suffix`: a kernel variant (the same -D flags tools/variants.sh hands to nvcc), built beside the default
+    out = LIB_RASTER_EMU.replace(".so", suffix + ".so") if suffix else LIB_RASTER_EMU
+    if not force and _newer(out, deps):
+        return out
+    cmd = [_host_cxx(), "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w"] + list(extra) + [
+           "-I", os.path.join(REPO, "tests", "native", "emu"), "-I", os.path.join(REPO, "include"), "-o", out, src]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
-    return LIB_RASTER_EMU
+    return out

@@ -255,3 +255,17 @@ def test_shared_reciprocal_division(emu):
             run(emu, scenes.fuzzy_circles(120, 160, 120, 4, 40, 9))
     finally:
         emu.raster_emu_set_rcp_error(0)
+
+
+def test_kernel_variant_unpaired_colour_loop():
+    """A compile-time variant checked the same way (-DGUDNI_EVAL_PAIR=0: one stack per lane in the colour
+    evaluation, the loop the default build does not contain) — what tools/variants.sh builds for the GPU can be
+    held to the oracle here first."""
+    L = ctypes.CDLL(_build.build_raster_emu(extra=("-DGUDNI_EVAL_PAIR=0",), suffix="_evalpair0"))
+    c = ctypes
+    L.raster_emu_frame.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int,
+                                   c.POINTER(CSpec), c.c_void_p, c.c_int64, c.c_void_p, c.c_void_p, c.c_int, c.c_int64,
+                                   c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
+    run(L, scenes.translucent_stack())
+    run(L, scenes.fuzzy_circles(150, 200, 150, 4, 40, 6))
+    run(L, scenes.picture_scene(320, 300, flowers_size=(350, 200)))
