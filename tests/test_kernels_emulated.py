@@ -269,3 +269,12 @@ def test_kernel_variant_unpaired_colour_loop():
     run(L, scenes.translucent_stack())
     run(L, scenes.fuzzy_circles(150, 200, 150, 4, 40, 6))
     run(L, scenes.picture_scene(320, 300, flowers_size=(350, 200)))
+
+
+def test_device_derived_spec(emu, emu_scene):
+    """The RasterSpec the reference would derive from the B200's OpenCL device (1,024-pixel tiles, 1,024 threads
+    per tile, MAXTHRESHOLDS 2,853 — tests/test_reference_pin.py): 32 warps per tile, 1,024-pixel root tiles."""
+    spec = RasterSpec(1024, 1024, 1024, 2853, 2851, 127)
+    run(emu, scenes.fuzzy_circles(150, 300, 200, 4, 40, 6), spec)
+    run_scene(emu_scene, scenes.mixed_bag(80, 260, 180, 7003), 3, spec)
+    run_scene(emu_scene, scenes.fuzzy_circles(60, 1100, 600, 10, 80, 8), 2, spec)

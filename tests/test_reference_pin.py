@@ -128,3 +128,18 @@ def test_mixed_bag(case):
     w, h = int(rng.integers(20, 700)), int(rng.integers(20, 500))
     scene = scenes.mixed_bag(int(rng.integers(1, 300)), w, h, 7000 + case)
     assert_identical(*both(scene, SPEC_64 if case % 3 == 0 else None))
+
+
+DEVICE_SPEC = RasterSpec(max_tile_size=1024, threads_per_tile=1024, max_tiles_per_call=1024, max_thresholds=2853,
+                         max_strands_per_tile=2851)
+
+
+def test_the_spec_the_reference_derives_on_this_gpu():
+    """determineRasterSpec (OpenCL/Setup.hs:71-87) on the B200's OpenCL device (profiles/r1_opencl_reference.json:
+    max work-group size 1024, max allocation 47,875,719,168 bytes): tile = threads = tiles per call = 1024,
+    maxThresholds = 47875719168 div (1024^2 * 16) = 2853.  The canonical spec of the benchmarks is smaller; this
+    is the one an unmodified Gudni would run with here."""
+    assert 47875719168 // (1024 ** 2 * 16) == DEVICE_SPEC.max_thresholds
+    assert_identical(*both(scenes.fuzzy_circles(2000, 1500, 1100, 5, 50, 3), DEVICE_SPEC))
+    assert_identical(*both(scenes.mixed_bag(200, 1300, 900, 11), DEVICE_SPEC))
+    assert_identical(*both(scenes.picture_scene(1100, 1030), DEVICE_SPEC))
