@@ -278,3 +278,35 @@ def test_device_derived_spec(emu, emu_scene):
     run(emu, scenes.fuzzy_circles(150, 300, 200, 4, 40, 6), spec)
     run_scene(emu_scene, scenes.mixed_bag(80, 260, 180, 7003), 3, spec)
     run_scene(emu_scene, scenes.fuzzy_circles(60, 1100, 600, 10, 80, 8), 2, spec)
+
+
+def test_threshold_overflow_is_counted_like_the_oracle(emu):
+    """MAXTHRESHOLDS = 16 and a stack of thin slanted rectangles over the left half of the canvas: those columns
+    overflow (undefined behaviour in the reference, App. B #9).  The kernels report exactly the threads the
+    oracle flags and leave every other column's pixels exact."""
+    from gudni_b200.scene import SceneBuilder
+    spec = RasterSpec(max_thresholds=16)
+    b = SceneBuilder(32, 96, (1.0, 1.0, 1.0, 1.0))
+    for i in range(40):
+        b.shape(b.solid(0.1, 0.2, 0.8, 0.5), [scenes._straight_outline([(0.0, 2.0 * i + 1.0), (15.5, 2.0 * i + 1.6),
+                                                                        (15.5, 2.0 * i + 2.4), (0.0, 2.0 * i + 1.8)])])
+    b.rectangle(b.solid(0.9, 0.1, 0.1, 0.7), 10.0, 60.0, [("translate", 19.3, 11.7)])
+    scene = b.freeze()
+    ref = oracle.render(scene, spec, taps=True)
+    assert 0 < ref.overflow_threads < 32
+    job = ref.jobs[0]
+    assert len(ref.jobs) == 1
+    out = np.zeros((scene.height, scene.width), np.uint32)
+    stats = np.zeros(4, np.int64)
+    g = np.ascontiguousarray(scene.geometry)
+    s = np.ascontiguousarray(scene.substances, np.float32)
+    bg = np.ascontiguousarray(scene.background, np.float32)
+    base = np.ascontiguousarray(job.tiles["column_allocation"].astype(np.int32))
+    tiles, shapes = np.ascontiguousarray(job.tiles), np.ascontiguousarray(job.shapes)
+    cs = spec.to_c()
+    emu.raster_emu_frame(g.ctypes.data, g.nbytes, s.ctypes.data, None, None, bg.ctypes.data, scene.width, scene.height,
+                         ctypes.byref(cs), shapes.ctypes.data, len(shapes), tiles.ctypes.data, base.ctypes.data, len(tiles),
+                         job.columns, out.ctypes.data, None, None, stats.ctypes.data)
+    assert stats[2] == ref.overflow_threads
+    written = ref.image != 0                       # the oracle leaves an overflowed thread's pixels untouched
+    assert written.any() and np.array_equal(out[written], ref.image[written])
