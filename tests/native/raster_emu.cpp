@@ -12,6 +12,8 @@
 
 namespace cuemu {
 int rcpUlpError = 0;
+int scheduleMode = 0;              // 0: lanes in ascending order, 1: descending, 2: a fresh pseudo-random order every pass
+static uint64_t scheduleRng = 0x9E3779B97F4A7C15ull;
 State S;
 unsigned char dynamicShared[228 * 1024];
 static void (*g_entry)(void*);
@@ -47,9 +49,17 @@ void runBlock(void (*entry)(void*), void* args, dim3 grid, dim3 block, uint3 bid
         makecontext(&f.ctx, trampoline, 0);
     }
     size_t remaining = n;
+    std::vector<size_t> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = scheduleMode == 1 ? n - 1 - i : i;
     while (remaining) {
         S.progress = false;
-        for (size_t i = 0; i < n; i++) {
+        if (scheduleMode == 2)      // between two rendezvous points the threads run in an arbitrary order, as on hardware:
+            for (size_t i = n; i > 1; i--) {   // code that needs a __syncwarp it does not have shows up as a wrong image
+                scheduleRng = scheduleRng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[i - 1], order[(scheduleRng >> 33) % i]);
+            }
+        for (size_t k = 0; k < n; k++) {
+            const size_t i = order[k];
             Fiber& f = S.fibers[i];
             if (f.done) continue;
             S.cur = &f;
@@ -230,6 +240,9 @@ extern "C" {
 // 0 restores the shim's sizing rule.  A store that is too small makes the generate kernel hand whole warps to
 // the replay kernel (raster_warp.cuh generateWarp): slow, not wrong.
 void raster_emu_set_store_entries(size_t n) { g_storeEntriesOverride = n; }
+
+// order in which the emulator runs the threads of a CTA between rendezvous points (see runBlock)
+void raster_emu_set_schedule(int mode) { cuemu::scheduleMode = mode; }
 
 // ulps by which the modelled rcp.approx misses the correctly rounded reciprocal (0, +-1, +-2 ...)
 void raster_emu_set_rcp_error(int ulps) { cuemu::rcpUlpError = ulps; }

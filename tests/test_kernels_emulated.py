@@ -310,3 +310,22 @@ def test_threshold_overflow_is_counted_like_the_oracle(emu):
     assert stats[2] == ref.overflow_threads
     written = ref.image != 0                       # the oracle leaves an overflowed thread's pixels untouched
     assert written.any() and np.array_equal(out[written], ref.image[written])
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["descending", "shuffled"])
+def test_thread_order_between_rendezvous_points_does_not_matter(emu, emu_scene, mode):
+    """A poor man's race check.  The emulator runs each thread until it reaches a shuffle, ballot, __syncwarp or
+    __syncthreads; in which order the threads get there is arbitrary on hardware.  With the lanes run in
+    descending order, or in a fresh pseudo-random order on every scheduling pass, every kernel still produces
+    the same bits — shared-memory hand-offs (colour cache lines, pending list, queue windows, CTA scans) are all
+    behind the synchronisation they need."""
+    emu.raster_emu_set_schedule.argtypes = [ctypes.c_int]
+    emu.raster_emu_set_schedule(mode)
+    try:
+        run(emu, scenes.translucent_stack())
+        run(emu, scenes.fuzzy_circles(150, 200, 150, 4, 40, 6))
+        run(emu, scenes.thin_rectangles(150, width=256, height=256, spacing=1.5, thickness=0.7, one_shape=True))
+        run_scene(emu_scene, scenes.mixed_bag(100, 300, 200, 7003), 3)
+        run_scene(emu_scene, scenes.fuzzy_circles(400, 150, 130, 5, 40, 0x1234), 2, RasterSpec(64, 64, 64, 256, 254, 127))
+    finally:
+        emu.raster_emu_set_schedule(0)
