@@ -58,12 +58,18 @@ constexpr int kPendingCap = GUDNI_PENDING_CAP;   // stacks waiting to be composi
 #define GUDNI_PENDING_FLUSH (GUDNI_EVAL_PAIR ? 48 : 27)
 #endif
 constexpr int kPendingFlush = GUDNI_PENDING_FLUSH;      // composite when this many are waiting (one per lane, most lanes busy)
-constexpr int kLogCap = GUDNI_EVAL_PAIR ? 72 : 40;            // per-lane log entries between flushes
+#ifndef GUDNI_LOG_CAP
+#define GUDNI_LOG_CAP (GUDNI_EVAL_PAIR ? 72 : 40)
+#endif
+constexpr int kLogCap = GUDNI_LOG_CAP;            // per-lane log entries between flushes
 #ifndef GUDNI_STORE_SLACK
 #define GUDNI_STORE_SLACK 8
 #endif
 constexpr int kStoreSlack = GUDNI_STORE_SLACK;   // free store entries in front of every queue (see HeadQueue)
-constexpr int kLinelessSlots = 64;
+#ifndef GUDNI_LINELESS_SLOTS
+#define GUDNI_LINELESS_SLOTS 64
+#endif
+constexpr int kLinelessSlots = GUDNI_LINELESS_SLOTS;   // hash slots for pending stacks without a cache line (power of two, at most 128)
 constexpr uint8_t kLinelessNone = 0xFF;
 constexpr uint8_t kLogInline = 0xFF;   // entry carries its colour
 constexpr uint8_t kLogPixelEnd = 0x7F; // markers kLogPixelEnd + n, n = 1 .. kMaxBlankRun: store the pixel n times
