@@ -75,7 +75,9 @@ struct Fiber {
     uint3 tid;
     int warp, lane;
     bool done;
+    int wait;      // what the fiber is blocked on (kWait*): the scheduler only switches to fibers that can go on
 };
+enum { kWaitNone, kWaitWarpFree, kWaitWarpResult, kWaitBarrierFree, kWaitBarrier };
 struct WarpSync {
     uint32_t arrived, release;      // lanes that deposited / lanes that still have to pick their result up
     uint64_t vals[32], results[32];
@@ -97,6 +99,7 @@ extern State S;
 extern unsigned char dynamicShared[228 * 1024] __attribute__((aligned(128)));
 
 inline void yield() { swapcontext(&S.cur->ctx, &S.scheduler); }
+inline void yieldOn(int wait) { S.cur->wait = wait; yield(); S.cur->wait = kWaitNone; }
 inline uint32_t liveMask(int warp) {
     uint32_t m = 0;
     for (int l = 0; l < 32; l++) {
@@ -142,7 +145,7 @@ inline uint64_t collective(int op, uint32_t mask, uint64_t value, int arg) {
     Fiber* f = S.cur;
     WarpSync& w = S.warps[f->warp];
     const uint32_t bit = 1u << f->lane;
-    while (w.release) yield();                    // the previous collective is still handing out results
+    while (w.release) yieldOn(kWaitWarpFree);      // the previous collective is still handing out results
     if (w.arrived && w.op != op) {
         // lanes of one warp sitting in different collectives: legal only if the masks are disjoint; this
         // code base always converges first, so report it
@@ -156,7 +159,7 @@ inline uint64_t collective(int op, uint32_t mask, uint64_t value, int arg) {
     w.arrived |= bit;
     S.progress = true;
     tryComplete(f->warp);
-    while (!(w.release & bit)) yield();
+    while (!(w.release & bit)) yieldOn(kWaitWarpResult);
     const uint64_t r = w.results[f->lane];
     w.release &= ~bit;
     S.progress = true;
@@ -164,7 +167,7 @@ inline uint64_t collective(int op, uint32_t mask, uint64_t value, int arg) {
 }
 inline void syncthreads() {
     // two-phase CTA barrier: barArrived counts deposits, barRelease the pick-ups still owed
-    while (S.barRelease) yield();
+    while (S.barRelease) yieldOn(kWaitBarrierFree);
     S.barArrived++;
     S.progress = true;
     for (;;) {
@@ -172,7 +175,7 @@ inline void syncthreads() {
         unsigned live = 0;
         for (const Fiber& f : S.fibers) live += !f.done;
         if (S.barArrived == live) { S.barRelease = live; S.barArrived = 0; break; }
-        yield();
+        yieldOn(kWaitBarrier);
     }
     S.barRelease--;
     S.progress = true;
@@ -186,6 +189,22 @@ inline float rcpApprox(float d) {
     float r = (float)(1.0 / (double)d);
     for (int i = 0; i < (rcpUlpError < 0 ? -rcpUlpError : rcpUlpError); i++) r = nextafterf(r, rcpUlpError < 0 ? 0.0f : INFINITY);
     return r;
+}
+
+// can a blocked fiber make progress if it is switched to now?
+inline bool canRun(const Fiber& f) {
+    switch (f.wait) {
+        case kWaitWarpFree: return S.warps[f.warp].release == 0;
+        case kWaitWarpResult: return (S.warps[f.warp].release & (1u << f.lane)) != 0;
+        case kWaitBarrierFree: return S.barRelease == 0;
+        case kWaitBarrier: {
+            if (S.barRelease) return true;
+            unsigned live = 0;
+            for (const Fiber& g : S.fibers) live += !g.done;
+            return S.barArrived == live;        // a thread that finished may have completed the barrier
+        }
+        default: return true;
+    }
 }
 
 template <class T> inline uint64_t pack(T v) { uint64_t u = 0; static_assert(sizeof(T) <= 8, "shuffle operand"); memcpy(&u, &v, sizeof(T)); return u; }

@@ -42,6 +42,7 @@ void runBlock(void (*entry)(void*), void* args, dim3 grid, dim3 block, uint3 bid
         f.warp = (int)(i / 32);
         f.lane = (int)(i % 32);
         f.done = false;
+        f.wait = kWaitNone;
         getcontext(&f.ctx);
         f.ctx.uc_stack.ss_sp = f.stack.data();
         f.ctx.uc_stack.ss_size = f.stack.size();
@@ -61,7 +62,7 @@ void runBlock(void (*entry)(void*), void* args, dim3 grid, dim3 block, uint3 bid
         for (size_t k = 0; k < n; k++) {
             const size_t i = order[k];
             Fiber& f = S.fibers[i];
-            if (f.done) continue;
+            if (f.done || !canRun(f)) continue;
             S.cur = &f;
             S.switches++;
             swapcontext(&S.scheduler, &f.ctx);
