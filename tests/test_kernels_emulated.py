@@ -204,7 +204,8 @@ def test_degenerate_outlines(emu_scene):
     run_scene(emu_scene, scene, 2)
 
 
-def test_strips_reassemble_the_frame(emu_scene):
+@pytest.mark.parametrize("level", [2, 3])
+def test_strips_reassemble_the_frame(emu_scene, level):
     """gudni_b200_frame_strip on the kernels' side: the binning kernels skip root tiles outside the strip, the
     raster kernels' threads outside it are inactive.  Three strips of whole root-tile rows (64-pixel tiles)
     rendered separately into one canvas give the frame, all entries passed to every strip."""
@@ -217,6 +218,7 @@ def test_strips_reassemble_the_frame(emu_scene):
     e = np.ascontiguousarray(scene.entries)
     s = np.ascontiguousarray(scene.substances, np.float32)
     bg = np.ascontiguousarray(scene.background, np.float32)
+    raw = [np.ascontiguousarray(a) for a in scene.raw]
     canvas = np.full((scene.height, scene.width), 0xDEADBEEF, np.uint32)
     sizes, stats = np.zeros(5, np.int64), np.zeros(4, np.int64)
     cs = spec.to_c()
@@ -225,9 +227,15 @@ def test_strips_reassemble_the_frame(emu_scene):
     try:
         for rows in ((0, 64), (64, 192), (192, 230)):
             L.raster_emu_set_strip(*rows)
-            rc = L.raster_emu_scene(ptr(g), g.nbytes, ptr(e), len(e), None, 0, None, None, None, ptr(s), None, None,
-                                    bg.ctypes.data, scene.width, scene.height, ctypes.byref(cs), canvas.ctypes.data,
-                                    None, 0, None, 0, None, 0, None, 0, None, None, 0, sizes.ctypes.data, stats.ctypes.data)
+            if level == 2:
+                rc = L.raster_emu_scene(ptr(g), g.nbytes, ptr(e), len(e), None, 0, None, None, None, ptr(s), None, None,
+                                        bg.ctypes.data, scene.width, scene.height, ctypes.byref(cs), canvas.ctypes.data,
+                                        None, 0, None, 0, None, 0, None, 0, None, None, 0, sizes.ctypes.data, stats.ctypes.data)
+            else:     # every strip builds the strands of the whole scene, then bins its own rows
+                rc = L.raster_emu_scene(None, 0, None, 0, ptr(raw[0]), len(raw[0]), ptr(raw[1]), ptr(raw[2]), ptr(raw[3]), ptr(s),
+                                        None, None, bg.ctypes.data, scene.width, scene.height, ctypes.byref(cs),
+                                        canvas.ctypes.data, None, 0, None, 0, None, 0, None, 0, None, None, 0,
+                                        sizes.ctypes.data, stats.ctypes.data)
             assert rc == 0
             total += int(stats[0])
             # rows of the other strips are untouched so far or already final
