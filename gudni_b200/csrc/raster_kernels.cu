@@ -150,10 +150,15 @@ __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, 
 
 // Counting sort of the launch's tiles by shape count, descending (one CTA; 256 bins, counts >= 255
 // share the first bin).  Longest-processing-time-first order for the persistent kernels.
-__global__ void __launch_bounds__(1024) tile_order_kernel(const gudni_tile* __restrict__ tiles, int tileBase, int nTiles,
-                                                          uint32_t* __restrict__ order) {
+// It is also where a frame whose geometry holds a point at infinity is defused (kCntNonFinite, set by
+// strand_bounds_kernel earlier on the stream): the tiles of the launch lose their shape lists, so the
+// raster kernels that follow never walk a strand and only paint background; frame_end reports the error.
+__global__ void __launch_bounds__(1024) tile_order_kernel(gudni_tile* __restrict__ tiles, int tileBase, int nTiles,
+                                                          uint32_t* __restrict__ order, const unsigned long long* __restrict__ counters) {
     __shared__ unsigned int bins[256];
     __shared__ unsigned int starts[256];
+    if (counters[kCntNonFinite])
+        for (int i = threadIdx.x; i < nTiles; i += blockDim.x) tiles[tileBase + i].shape_count = 0u;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) bins[i] = 0u;
     __syncthreads();
     for (int i = threadIdx.x; i < nTiles; i += blockDim.x)
@@ -173,22 +178,25 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const gudni_tile* __re
 // (min y, max y) over all points of every strand of `count` shape records (`stride` bytes apart, each
 // starting with {u64 tag, u32 geo_start, u32 num_strands}); strand layout K.cl:1365-1376.
 __global__ void strand_bounds_kernel(const uint8_t* __restrict__ geometry, const uint8_t* __restrict__ records, int stride,
-                                     int count, float2* __restrict__ bounds) {
+                                     int count, float2* __restrict__ bounds, unsigned long long* __restrict__ counters) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
+    bool infinite = false;
     const uint4 rec = __ldg(reinterpret_cast<const uint4*>(records + (size_t)i * stride));
     const uint8_t* strand = geometry + 16ull * rec.z;
     for (uint32_t s = 0; s < rec.w; s++) {
         const uint32_t size = __ldg(reinterpret_cast<const uint32_t*>(strand)) & 0xFFFFu;   // in 8-byte units
         float lo = FLT_MAX, hi = -FLT_MAX;
         for (uint32_t k = 1; k < size; k++) {
-            const float y = __ldg(reinterpret_cast<const float*>(strand + 8 * k + 4));
-            lo = fminf(lo, y);
-            hi = fmaxf(hi, y);
+            const float2 p = __ldg(reinterpret_cast<const float2*>(strand + 8 * k));
+            lo = fminf(lo, p.y);
+            hi = fmaxf(hi, p.y);
+            infinite |= fabsf(p.x) == INFINITY || fabsf(p.y) == INFINITY;   // NaN terminates (and compares false)
         }
         bounds[(size_t)(strand - geometry) >> 4] = make_float2(lo, hi);
         strand += 8u * size;
     }
+    if (infinite) counters[kCntNonFinite] = 1ull;
 }
 
 // div3 against the compiler's IEEE division on pseudo-random operands (and the edge cases around
@@ -226,8 +234,9 @@ __global__ void selftest_div3_kernel(unsigned long long n, unsigned long long se
 namespace gudni_launch {
 int strandBounds(gudni_ctx* ctx, const void* geometry, const void* records, int stride, int count, float2* bounds) {
     if (count <= 0) return GUDNI_OK;
+    unsigned long long* counters = ctx->counters.as<unsigned long long>();
     strand_bounds_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(geometry),
-                                                                     static_cast<const uint8_t*>(records), stride, count, bounds);
+                                                                     static_cast<const uint8_t*>(records), stride, count, bounds, counters);
     ctx->launches++;
     GUDNI_CUDA_TRY(ctx, cudaGetLastError());
     return GUDNI_OK;
@@ -261,7 +270,7 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     const long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
     const int genGrid = (int)std::min<long long>((long long)genCtasPerSm * numSms, (units + kGenWarpsPerCta - 1) / kGenWarpsPerCta);
     const int sweepGrid = (int)std::min<long long>((long long)sweepCtasPerSm * numSms, (units + kSweepWarpsPerCta - 1) / kSweepWarpsPerCta);
-    tile_order_kernel<<<1, 1024, 0, ctx->stream>>>(P.tiles, tileBase, nTiles, const_cast<uint32_t*>(P.tileOrder));
+    tile_order_kernel<<<1, 1024, 0, ctx->stream>>>(const_cast<gudni_tile*>(P.tiles), tileBase, nTiles, const_cast<uint32_t*>(P.tileOrder), P.counters);
     ctx->launches++;
     raster_generate_kernel<<<genGrid, kGenWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
     raster_sweep_kernel<<<sweepGrid, kSweepWarpsPerCta * 32, sweepSmem, ctx->stream>>>(P, tileBase, nTiles);

@@ -476,6 +476,8 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     fprintf(stderr, "[stats] records %llu ready-hits %llu pending-hits %llu new %llu slow %llu rounds %llu flushes %llu logged %llu\n",
             counters[8], counters[9], counters[10], counters[11], counters[12], counters[13], counters[14], counters[15]);
 #endif
+    if (counters[gudni_dev::kCntNonFinite])
+        return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "geometry holds a point at infinity: the reference's curve bisection does not terminate on it; nothing was rasterized");
     if (binCounters[4])
         return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "a minimum-size tile lists more than 65535 shapes: unsupported by the raster kernels");
     gudni_stats s{};

@@ -180,7 +180,11 @@ int gudni_b200_raster_scene(gudni_ctx* ctx, const gudni_shape_entry* entries, in
 /* Replaces the OutputPtr read-back (OpenCL/Instances.hs:60-75): waits for the frame, copies the
  * BGRA8 words (B | G<<8 | R<<16 | 0xFF<<24) of the context's rows into `out_bgra`
  * (width * (row_end-row_begin) words, may be NULL to leave the frame on the device) and fills
- * `stats` (may be NULL). */
+ * `stats` (may be NULL).
+ * Returns GUDNI_ERR_ARGUMENT — and a bitmap that means nothing — if the frame's geometry held a point at
+ * +-infinity: the curve bisection of Kernels.cl:1226-1258 does not terminate on one (the reference's kernels
+ * hang), so the raster kernels were not let near it.  NaN and large finite coordinates render as in the
+ * reference.  The context stays usable. */
 int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats);
 
 /* Device-side access for callers that keep data on the GPU (bench, multi-GPU gather).  The frame

@@ -122,7 +122,8 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
     std::vector<uint32_t> spillHdr((size_t)spillSlots * in.spec->max_thresholds);
     P.geometry = static_cast<const uint8_t*>(in.geometry);
     P.shapes = shapes;
-    P.tiles = tiles;
+    std::vector<gudni_tile> tilesCopy(tiles, tiles + std::max(nTiles, 0));   // the shim's device copy (tile_order_kernel may edit it)
+    P.tiles = tilesCopy.data();
     P.tileThreadBase = threadBase;
     P.substances = reinterpret_cast<const float4*>(in.substances);
     P.pictureData = in.pictureBytes;
@@ -153,8 +154,8 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
     if (nTiles > 0) {
         if (nBoundsRecords > 0)
             cuemu::launch(strand_bounds_kernel, dim3((unsigned)((nBoundsRecords + 255) / 256)), dim3(256), P.geometry,
-                          static_cast<const uint8_t*>(boundsRecords), boundsStride, (int)nBoundsRecords, bounds.data());
-        cuemu::launch(tile_order_kernel, dim3(1), dim3(256), tiles, 0, nTiles, order.data());
+                          static_cast<const uint8_t*>(boundsRecords), boundsStride, (int)nBoundsRecords, bounds.data(), counters.data());
+        cuemu::launch(tile_order_kernel, dim3(1), dim3(256), tilesCopy.data(), 0, nTiles, order.data(), counters.data());
         cuemu::launch(raster_generate_kernel, dim3(2), dim3(kGenWarpsPerCta * 32), P, 0, nTiles);
         cuemu::launch(raster_sweep_kernel, dim3(2), dim3(kSweepWarpsPerCta * 32), P, 0, nTiles);
         cuemu::launch(raster_spill_kernel, dim3(1), dim3(spillSlots), P, spillThr.data(), spillHdr.data(), spillSlots);
@@ -165,6 +166,7 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
         stats[1] = (int64_t)counters[kCntSpilled];
         stats[2] = (int64_t)counters[kCntOverflow];
         stats[3] = (int64_t)cuemu::S.switches;
+        stats[4] = (int64_t)counters[kCntNonFinite];
     }
 }
 
@@ -282,8 +284,8 @@ uint64_t raster_emu_selftest_div3(uint64_t n, uint64_t seed) {
 void raster_emu_set_strip(int row_begin, int row_end) { g_rowBegin = row_begin; g_rowEnd = row_end; }
 
 // Level 1: the jobs' shapes and tiles laid end to end as the shim lays them (shape_start rebased,
-// thread_base = first column-thread of each tile).  stats[0..3] = thresholds, spilled threads, overflowed
-// threads, context switches.
+// thread_base = first column-thread of each tile).  stats[0..4] (room for 8) = thresholds, spilled threads, overflowed
+// threads, context switches, the infinite-coordinate flag.
 int raster_emu_frame(const void* geometry, size_t geometry_bytes, const float* substances, const uint8_t* picture_bytes,
                      const gudni_picture_use* picture_uses, const float* background, int width, int height,
                      const gudni_spec* spec, const gudni_shape* shapes, int64_t n_shapes, const gudni_tile* tiles,

@@ -28,13 +28,11 @@ def emu():
     return L
 
 
-def run(L, scene, spec=CANONICAL_SPEC):
+def emulate_frame(L, scene, jobs, spec=CANONICAL_SPEC):
     """Level 1 of the ABI the way the shim lays a frame out: all jobs end to end."""
-    ref = oracle.render(scene, spec, taps=True)
-    assert ref.overflow_threads == 0
     tiles, shapes, base = [], [], []
     shape_base = column_base = 0
-    for job in ref.jobs:
+    for job in jobs:
         t = job.tiles.copy()
         t["shape_start"] += shape_base
         base.append((column_base + job.tiles["column_allocation"]).astype(np.int32))
@@ -48,7 +46,7 @@ def run(L, scene, spec=CANONICAL_SPEC):
     out = np.zeros((scene.height, scene.width), np.uint32)
     counts = np.zeros(column_base, np.int32)
     bits = np.zeros(column_base, np.int32)
-    stats = np.zeros(4, np.int64)
+    stats = np.zeros(8, np.int64)
     g = np.ascontiguousarray(scene.geometry)
     s = np.ascontiguousarray(scene.substances, np.float32)
     p = np.ascontiguousarray(scene.picture_bytes)
@@ -59,6 +57,13 @@ def run(L, scene, spec=CANONICAL_SPEC):
     rc = L.raster_emu_frame(ptr(g), g.nbytes, ptr(s), ptr(p), ptr(u), bg.ctypes.data, scene.width, scene.height,
                             ctypes.byref(cs), shapes.ctypes.data, shape_base, tiles.ctypes.data, base.ctypes.data,
                             len(tiles), column_base, out.ctypes.data, counts.ctypes.data, bits.ctypes.data, stats.ctypes.data)
+    return rc, out, counts, bits, stats
+
+
+def run(L, scene, spec=CANONICAL_SPEC):
+    ref = oracle.render(scene, spec, taps=True)
+    assert ref.overflow_threads == 0
+    rc, out, counts, bits, stats = emulate_frame(L, scene, ref.jobs, spec)
     assert rc == 0
     assert np.array_equal(counts, np.concatenate(ref.n_thresholds)), "per-thread threshold counts"
     assert np.array_equal(bits, np.concatenate(ref.shape_bits)), "per-thread shape bits"
@@ -76,6 +81,34 @@ CATALOGUE = [scenes.tiny_square, scenes.medium_square, scenes.full_rectangle, sc
 @pytest.mark.parametrize("make", CATALOGUE, ids=lambda f: f.__name__)
 def test_catalogue_scenes(emu, make):
     run(emu, make())
+
+
+@pytest.mark.parametrize("value", [np.inf, -np.inf])
+@pytest.mark.parametrize("coord", [0, 1], ids=["x", "y"])
+def test_infinite_coordinate_is_refused_not_rasterized(emu, value, coord):
+    """A point at +-infinity makes the bisection of Kernels.cl:1226-1258 loop for ever (the reference's own kernels
+    hang on it).  strand_bounds_kernel flags it, tile_order_kernel empties the shape lists of the launch so that the
+    raster kernels never walk a strand, and gudni_b200_frame_end turns the flag into GUDNI_ERR_ARGUMENT.  The jobs come from the finite scene: the oracle
+    would not return on the poisoned one."""
+    scene = scenes.medium_square()
+    jobs = oracle.build_raster_jobs(scene)
+    scene.geometry = scene.geometry.copy()
+    points = scene.geometry.view(np.float32)
+    points[2 * 2 + coord] = value            # record 0 is the strand header; unit 2 is an on-curve point
+    rc, out, counts, bits, stats = emulate_frame(emu, scene, jobs)
+    assert rc == 0
+    assert stats[4] == 1 and stats[0] == 0 and stats[1] == 0
+    assert (counts[counts >= 0] == 0).all()            # background only: no thread generated a threshold
+
+
+def test_nan_and_huge_coordinates_still_rasterize(emu):
+    """NaN and finite values up to 3e38 terminate in the reference, so they are not refused (bits equal the oracle's)."""
+    for value in (np.nan, 3.0e38, -3.0e38):
+        scene = scenes.medium_square()
+        scene.geometry = scene.geometry.copy()
+        scene.geometry.view(np.float32)[2 * 2] = value
+        stats = run(emu, scene)
+        assert stats[4] == 0
 
 
 def test_circles_rectangles_pictures(emu):
@@ -137,7 +170,7 @@ def run_scene(L, scene, level, spec=CANONICAL_SPEC):
     counts = np.zeros(columns, np.int32)
     bits = np.zeros(columns, np.int32)
     sizes = np.zeros(5, np.int64)
-    stats = np.zeros(4, np.int64)
+    stats = np.zeros(8, np.int64)
     cs = spec.to_c()
     rc = L.raster_emu_scene(ptr(g) if level == 2 else None, g.nbytes if level == 2 else 0, ptr(e) if level == 2 else None,
                             len(e) if level == 2 else 0, ptr(raw[0]), len(raw[0]) if level == 3 else 0, ptr(raw[1]), ptr(raw[2]),
@@ -205,6 +238,39 @@ def test_degenerate_outlines(emu_scene):
 
 
 @pytest.mark.parametrize("level", [2, 3])
+def test_infinite_coordinate_is_refused_at_levels_2_and_3(emu_scene, level):
+    """Level 2: the poisoned heap arrives with finite boxes.  Level 3: the outline itself holds the infinite point; the
+    strand kernels (transform, box, knob splitting, reordering) get through it, the shapes whose box still meets the
+    canvas reach the heap, and the flag goes up there.  Either way no thread generates a threshold."""
+    L = emu_scene
+    scene = scenes.fuzzy_circles(20, 120, 100, 5, 30, 3)
+    ptr = lambda a: a.ctypes.data if a.size else None  # noqa: E731
+    s = np.ascontiguousarray(scene.substances, np.float32)
+    bg = np.ascontiguousarray(scene.background, np.float32)
+    cs = CANONICAL_SPEC.to_c()
+    for value in (np.inf, -np.inf):
+        for coord in (0, 1):
+            canvas = np.zeros((scene.height, scene.width), np.uint32)
+            sizes, stats = np.zeros(5, np.int64), np.zeros(8, np.int64)
+            if level == 2:
+                g = np.ascontiguousarray(scene.geometry).copy()
+                g.view(np.float32)[2 * 2 + coord] = value
+                e = np.ascontiguousarray(scene.entries)
+                rc = L.raster_emu_scene(ptr(g), g.nbytes, ptr(e), len(e), None, 0, None, None, None, ptr(s), None, None,
+                                        bg.ctypes.data, scene.width, scene.height, ctypes.byref(cs), canvas.ctypes.data,
+                                        None, 0, None, 0, None, 0, None, 0, None, None, 0, sizes.ctypes.data, stats.ctypes.data)
+            else:
+                raw = [np.ascontiguousarray(a).copy() for a in scene.raw]
+                raw[2].view(np.float32).reshape(-1)[coord] = value
+                rc = L.raster_emu_scene(None, 0, None, 0, ptr(raw[0]), len(raw[0]), ptr(raw[1]), ptr(raw[2]), ptr(raw[3]), ptr(s),
+                                        None, None, bg.ctypes.data, scene.width, scene.height, ctypes.byref(cs),
+                                        canvas.ctypes.data, None, 0, None, 0, None, 0, None, 0, None, None, 0,
+                                        sizes.ctypes.data, stats.ctypes.data)
+            assert rc == 0
+            assert stats[4] == 1 and stats[0] == 0 and stats[1] == 0, (level, value, coord, stats)
+
+
+@pytest.mark.parametrize("level", [2, 3])
 def test_strips_reassemble_the_frame(emu_scene, level):
     """gudni_b200_frame_strip on the kernels' side: the binning kernels skip root tiles outside the strip, the
     raster kernels' threads outside it are inactive.  Three strips of whole root-tile rows (64-pixel tiles)
@@ -220,7 +286,7 @@ def test_strips_reassemble_the_frame(emu_scene, level):
     bg = np.ascontiguousarray(scene.background, np.float32)
     raw = [np.ascontiguousarray(a) for a in scene.raw]
     canvas = np.full((scene.height, scene.width), 0xDEADBEEF, np.uint32)
-    sizes, stats = np.zeros(5, np.int64), np.zeros(4, np.int64)
+    sizes, stats = np.zeros(5, np.int64), np.zeros(8, np.int64)
     cs = spec.to_c()
     total = 0
     L.raster_emu_set_strip.argtypes = [ctypes.c_int, ctypes.c_int]
@@ -305,7 +371,7 @@ def test_threshold_overflow_is_counted_like_the_oracle(emu):
     job = ref.jobs[0]
     assert len(ref.jobs) == 1
     out = np.zeros((scene.height, scene.width), np.uint32)
-    stats = np.zeros(4, np.int64)
+    stats = np.zeros(8, np.int64)
     g = np.ascontiguousarray(scene.geometry)
     s = np.ascontiguousarray(scene.substances, np.float32)
     bg = np.ascontiguousarray(scene.background, np.float32)
