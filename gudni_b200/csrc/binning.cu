@@ -97,8 +97,13 @@ __device__ __forceinline__ bool overlaps(const float4 box, int L, int T, int R, 
 template <class F>
 __device__ __forceinline__ void forEachRoot(const BinParams& P, const float4 box, F&& f) {
     const int R = P.rootsPerSide, S = P.rootSize;
-    int tx0 = max(0, (int)floorf(box.x / (float)S) - 1), tx1 = min(R - 1, (int)floorf(box.z / (float)S) + 1);
-    int ty0 = max(0, (int)floorf(box.y / (float)S) - 1), ty1 = min(R - 1, (int)floorf(box.w / (float)S) + 1);
+    // candidate range, one root to spare on each side; clamped as floats, because a box may be far outside
+    // what an int holds (or infinite) and `overlaps`, like the reference, compares floats
+    const float last = (float)(R - 1);
+    const int tx0 = (int)fminf(fmaxf(floorf(box.x / (float)S) - 1.0f, 0.0f), last + 1.0f);
+    const int tx1 = (int)fmaxf(fminf(floorf(box.z / (float)S) + 1.0f, last), -1.0f);
+    const int ty0 = (int)fminf(fmaxf(floorf(box.y / (float)S) - 1.0f, 0.0f), last + 1.0f);
+    const int ty1 = (int)fmaxf(fminf(floorf(box.w / (float)S) + 1.0f, last), -1.0f);
     for (int ty = ty0; ty <= ty1; ty++) {
         if (!rootActive(P, ty)) continue;
         for (int tx = tx0; tx <= tx1; tx++)

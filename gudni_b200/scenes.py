@@ -390,3 +390,13 @@ def mixed_bag(n, width, height, seed, name=""):
             b.shape(sub, [_straight_outline([(x, y), (x + d[0], y + d[1]), (x + d[0] + nrm[0], y + d[1] + nrm[1])])],
                     is_picture=use_picture)
     return b.freeze()
+
+
+def huge_boxes(width=300, height=200):
+    """Translucent rectangles up to 4e12 pixels across, behind and in front of some circles: their boxes, divided by
+    the root tile size, are far outside int32, and the tile tree (Raster/TileTree.hs:120-139) compares floats."""
+    b = SceneBuilder(width, height, (0.9, 0.9, 0.9, 1.0), name="hugeBoxes")
+    b.rectangle(b.solid(0.1, 0.3, 0.8, 0.4), 4.0e12, 4.0e12, [("translate", -2.0e12, -2.0e12)])
+    b.fuzzy_circles(40, width, height, 5, 40, 0xB16)
+    b.rectangle(b.solid(0.8, 0.3, 0.1, 0.3), 3.0e12, 50.0, [("translate", -1.0e12, 70.0)])
+    return b.freeze()

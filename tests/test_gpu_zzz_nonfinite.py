@@ -1,4 +1,5 @@
-"""Geometry with a point at +-infinity.  The reference's curve bisection (Kernels.cl:1226-1258) does not terminate
+"""Coordinates at the far end of float32.  (1) Boxes beyond int32 root tiles are binned like any other.
+(2) Geometry with a point at +-infinity.  The reference's curve bisection (Kernels.cl:1226-1258) does not terminate
 on it — its own kernels hang — so the library refuses the frame instead: strand_bounds_kernel raises a flag,
 tile_order_kernel empties the shape lists of the launch, the raster kernels paint background only, and
 gudni_b200_frame_end returns GUDNI_ERR_ARGUMENT.  The context stays usable.
@@ -52,6 +53,17 @@ for level in (1, 2):
 r.close()
 print("REFUSED-AND-RECOVERED")
 """
+
+
+def test_boxes_beyond_int32_are_binned(rasterizer):
+    """Level 2 and 3 on a scene whose boxes, in root tiles, overflow an int32: tiles, shape lists, counts and pixels
+    against the oracle (the binning clamps its candidate range in float)."""
+    from gudni_b200 import scenes
+    from parity import level2_parity
+    scene = scenes.huge_boxes()
+    img, stats, ref = level2_parity(rasterizer, scene)
+    img3, stats3 = rasterizer.raster_outlines(0, scene)
+    assert (img3 == ref.image).all() and stats3.n_thresholds == ref.total_thresholds
 
 
 def test_infinite_coordinate_is_refused():

@@ -14,6 +14,7 @@ import numpy as np
 import pytest
 
 from gudni_b200 import _build, scenes
+from gudni_b200.scene import SceneBuilder
 from gudni_b200.formats import CANONICAL_SPEC, CSpec, RasterSpec, SHAPE_DTYPE
 from oracle import oracle
 
@@ -224,7 +225,6 @@ def test_degenerate_outlines(emu_scene):
     """Outlines of fewer than two curve pairs produce no strands (Strand.hs:175-177) but still count towards
     the shape's bounding box (onShape boxes the outlines first); a shape made only of such outlines is an entry
     without geometry."""
-    from gudni_b200.scene import SceneBuilder
     b = SceneBuilder(64, 48, (0.1, 0.2, 0.3, 1.0))
     red = b.solid(1, 0, 0, 0.5)
     square = np.array([[10, 10, 20, 10], [30, 10, 30, 20], [30, 30, 20, 30], [10, 30, 10, 20]], np.float32)
@@ -235,6 +235,12 @@ def test_degenerate_outlines(emu_scene):
     assert scene.entries["right"][0] == np.float32(51.0)
     run_scene(emu_scene, scene, 3)
     run_scene(emu_scene, scene, 2)
+
+
+@pytest.mark.parametrize("level", [2, 3])
+def test_boxes_beyond_int32_are_binned(emu_scene, level):
+    """Boxes that, divided by the root tile size, do not fit an int32 (binning.cu forEachRoot clamps in float)."""
+    run_scene(emu_scene, scenes.huge_boxes(), level)
 
 
 @pytest.mark.parametrize("level", [2, 3])
@@ -358,7 +364,6 @@ def test_threshold_overflow_is_counted_like_the_oracle(emu):
     """MAXTHRESHOLDS = 16 and a stack of thin slanted rectangles over the left half of the canvas: those columns
     overflow (undefined behaviour in the reference, App. B #9).  The kernels report exactly the threads the
     oracle flags and leave every other column's pixels exact."""
-    from gudni_b200.scene import SceneBuilder
     spec = RasterSpec(max_thresholds=16)
     b = SceneBuilder(32, 96, (1.0, 1.0, 1.0, 1.0))
     for i in range(40):

@@ -1,7 +1,7 @@
 """The kernels under sanitizers, CPU only: builds the host SIMT emulation of the CUDA kernels
 (tests/native/raster_emu.cpp) with -fsanitize=undefined or -fsanitize=address and runs the emulated-kernel
 scenarios of tests/test_kernels_emulated.py through it (catalogue, circles, pictures, both spill paths,
-levels 2 and 3).  Global and shared memory are host heap / static arrays there, so an out-of-bounds access or a
+levels 2 and 3, refused frames).  Global and shared memory are host heap / static arrays there, so an out-of-bounds access or a
 misaligned vector load in a kernel is reported like any host bug.
 
     python tools/emu_sanitize.py ubsan|asan
@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MODES = {"ubsan": (["-fsanitize=undefined", "-fno-sanitize-recover=undefined"], "libubsan.so", {}),
+MODES = {"ubsan": (["-fsanitize=undefined,float-cast-overflow", "-fno-sanitize-recover=undefined,float-cast-overflow"], "libubsan.so", {}),
          "asan": (["-fsanitize=address"], "libasan.so", {"ASAN_OPTIONS": "detect_leaks=0:detect_stack_use_after_return=0"})}
 
 
@@ -38,6 +38,13 @@ def scenario(lib_path):
     for level in (2, 3):
         T.run_scene(L, scenes.mixed_bag(100, 300, 200, 7003), level)
         T.run_scene(L, scenes.fuzzy_circles(400, 150, 130, 5, 40, 0x1234), level, RasterSpec(64, 64, 64, 256, 254, 127))
+    import numpy as np
+    # a point at infinity: strand_bounds_kernel's flag, tile_order_kernel emptying the launch's shape lists
+    T.test_infinite_coordinate_is_refused_not_rasterized(L, np.inf, 0)
+    T.test_infinite_coordinate_is_refused_not_rasterized(L, -np.inf, 1)
+    for level in (2, 3):
+        T.test_infinite_coordinate_is_refused_at_levels_2_and_3(L, level)
+        T.run_scene(L, scenes.huge_boxes(), level)       # boxes beyond int32 root tiles
     print("sanitized run complete: no reports")
 
 
