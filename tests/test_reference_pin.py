@@ -72,6 +72,18 @@ def test_catalogue_scenes(make):
     assert_identical(*both(make()))
 
 
+def test_coordinates_at_the_far_end_of_float32():
+    """Rectangles 4e12 pixels across, and a coordinate turned into NaN or +-3e38: the reference's kernels terminate on
+    all of them and the restatement produces the same bits.  (A point at infinity is the one thing they do not
+    terminate on — DESIGN section 7 — so it is not run.)"""
+    assert_identical(*both(scenes.huge_boxes()))
+    for value in (np.nan, 3.0e38, -3.0e38):
+        scene = scenes.medium_square()
+        scene.geometry = scene.geometry.copy()
+        scene.geometry.view(np.float32)[2 * 2] = value
+        assert_identical(*both(scene))
+
+
 @pytest.mark.parametrize("theta", [0.3, 0.4, 0.5, 0.625])
 @pytest.mark.parametrize("size", [100, 512])
 def test_s1_square(size, theta):
