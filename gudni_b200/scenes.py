@@ -400,3 +400,25 @@ def huge_boxes(width=300, height=200):
     b.fuzzy_circles(40, width, height, 5, 40, 0xB16)
     b.rectangle(b.solid(0.8, 0.3, 0.1, 0.3), 3.0e12, 50.0, [("translate", -1.0e12, 70.0)])
     return b.freeze()
+
+
+def far_shapes(n, width, height, seed):
+    """Seeded rectangles and circles whose size is log-uniform between 1 and 1e30 pixels, placed so that most of them
+    cross or cover the canvas — coordinates far beyond what an int or a pixel grid holds (fuzz fodder for the binning's
+    float compares and the kernels' arithmetic at the far end of float32)."""
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder(width, height, (0.9, 0.9, 0.9, 1.0), name=f"farShapes-{n}-{seed}")
+    for _ in range(n):
+        col = rng.uniform(0, 1, 3)
+        s = b.solid(float(col[0]), float(col[1]), float(col[2]), float(rng.uniform(0.2, 1.0)))
+        size = float(10.0 ** rng.uniform(0.0, 30.0))
+        x = float(rng.uniform(0, width) - size * rng.uniform(0, 1))
+        y = float(rng.uniform(0, height) - size * rng.uniform(0, 1))
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            b.rectangle(s, size, float(size * rng.uniform(0.01, 1.0)), [("translate", x, y)])
+        elif kind == 1:
+            b.rectangle(s, size, float(size * rng.uniform(0.01, 1.0)), [("translate", x, y), ("rotate", float(rng.uniform(0, 1)))])
+        else:
+            b.circle(s, [("translate", float(x + size / 2), float(y + size / 2)), ("scale", size / 2)])
+    return b.freeze()

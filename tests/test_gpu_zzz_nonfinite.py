@@ -60,10 +60,10 @@ def test_boxes_beyond_int32_are_binned(rasterizer):
     against the oracle (the binning clamps its candidate range in float)."""
     from gudni_b200 import scenes
     from parity import level2_parity
-    scene = scenes.huge_boxes()
-    img, stats, ref = level2_parity(rasterizer, scene)
-    img3, stats3 = rasterizer.raster_outlines(0, scene)
-    assert (img3 == ref.image).all() and stats3.n_thresholds == ref.total_thresholds
+    for scene in [scenes.huge_boxes()] + [scenes.far_shapes(12, 150, 110, 0xFA50 + seed) for seed in range(3)]:
+        img, stats, ref = level2_parity(rasterizer, scene)
+        img3, stats3 = rasterizer.raster_outlines(0, scene)
+        assert (img3 == ref.image).all() and stats3.n_thresholds == ref.total_thresholds, scene.name
 
 
 def test_infinite_coordinate_is_refused():

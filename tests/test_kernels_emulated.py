@@ -241,6 +241,8 @@ def test_degenerate_outlines(emu_scene):
 def test_boxes_beyond_int32_are_binned(emu_scene, level):
     """Boxes that, divided by the root tile size, do not fit an int32 (binning.cu forEachRoot clamps in float)."""
     run_scene(emu_scene, scenes.huge_boxes(), level)
+    for seed in range(3):         # sizes log-uniform up to 1e30 pixels
+        run_scene(emu_scene, scenes.far_shapes(12, 150, 110, 0xFA50 + seed), level)
 
 
 @pytest.mark.parametrize("level", [2, 3])

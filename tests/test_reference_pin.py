@@ -77,6 +77,8 @@ def test_coordinates_at_the_far_end_of_float32():
     all of them and the restatement produces the same bits.  (A point at infinity is the one thing they do not
     terminate on — DESIGN section 7 — so it is not run.)"""
     assert_identical(*both(scenes.huge_boxes()))
+    for seed in range(8):         # rectangles and circles of 1 to 1e30 pixels across the canvas
+        assert_identical(*both(scenes.far_shapes(12, 150, 110, 0xFA50 + seed)))
     for value in (np.nan, 3.0e38, -3.0e38):
         scene = scenes.medium_square()
         scene.geometry = scene.geometry.copy()

@@ -45,6 +45,8 @@ def scenario(lib_path):
     for level in (2, 3):
         T.test_infinite_coordinate_is_refused_at_levels_2_and_3(L, level)
         T.run_scene(L, scenes.huge_boxes(), level)       # boxes beyond int32 root tiles
+        for seed in range(12):                           # shapes of 1 to 1e30 pixels: no out-of-range float -> int anywhere
+            T.run_scene(L, scenes.far_shapes(12, 150, 110, 0xFA50 + seed), level)
     print("sanitized run complete: no reports")
 
 

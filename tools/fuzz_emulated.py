@@ -1,6 +1,7 @@
 """Long differential run, CPU only: the CUDA kernels under the host SIMT emulator (tests/native/raster_emu.cpp)
 vs the oracle on seeded random small scenes — levels 1, 2 and 3, several RasterSpecs.
-   python tools/fuzz_emulated.py <first case> <seconds>     prints one JSON line; MISMATCH <case> ... on a difference."""
+   python tools/fuzz_emulated.py <first case> <seconds> [--far]    prints one JSON line; MISMATCH <case> ... on a difference.
+--far: scenes of shapes up to 1e30 pixels across (the case number is printed first: run it under `timeout`)."""
 import ctypes
 import json
 import os
@@ -22,7 +23,12 @@ SPECS = [RasterSpec(), RasterSpec(64, 64, 64, 512, 510, 127), RasterSpec(32, 32,
          RasterSpec(128, 128, 128, 1024, 1022, 127), RasterSpec(1024, 1024, 1024, 2853, 2851, 127)]
 
 
+FAR = "--far" in sys.argv      # shapes up to 1e30 pixels across (scenes.far_shapes) instead of the ordinary mix
+
+
 def main():
+    if FAR:
+        sys.argv.remove("--far")
     case = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 60.0
     c = ctypes
@@ -36,8 +42,11 @@ def main():
     while time.time() - t0 < seconds:
         rng = np.random.default_rng(700000 + case)
         w, h = int(rng.integers(8, 160)), int(rng.integers(8, 120))
-        kind = int(rng.integers(0, 3))
-        if kind == 0:
+        kind = 3 if FAR else int(rng.integers(0, 3))
+        if kind == 3:
+            print("case", case, flush=True)      # a case that never returns is identified by the last line printed
+            sc = scenes.far_shapes(int(rng.integers(1, 30)), w, h, 830000 + case)
+        elif kind == 0:
             sc = scenes.mixed_bag(int(rng.integers(1, 120)), w, h, 800000 + case)
         elif kind == 1:
             sc = scenes.fuzzy_circles(int(rng.integers(1, 400)), w, h, float(rng.uniform(0.5, 5)), float(rng.uniform(5, 60)), 810000 + case)
