@@ -7,7 +7,8 @@
 // without replaying its one-shape-at-a-time insertion.  Two facts make a parallel restatement exact:
 //   (1) a shape reaches a node with box [L,R)x[T,B) iff  left < R && right > L && top < B &&
 //       bottom > T  (float compares against the integer cuts; every went-left cut on the path is
-//       >= R and every went-right cut is <= L, and canvas culling supplies the outermost bounds);
+//       >= R and every went-right cut is <= L; the outermost bounds are never tested by the tree —
+//       canvas culling supplies them — and forEachRoot leaves them untested too);
 //   (2) a leaf splits iff the shapes that reach it number >= 127 or their strands sum to
 //       >= maxStrandsPerTile (checkTileSpace :161-166 fails for some prefix iff it fails for the
 //       whole set, counts being monotone) and the leaf is still larger than 8 px in its split axis.
@@ -89,25 +90,26 @@ __device__ __forceinline__ bool rootActive(const BinParams& P, uint32_t ty) {
     return top >= P.rowBegin && top < P.rowEnd;
 }
 
-// fact (1) above, with the reference's float compares (TileTree.hs:120-139)
-__device__ __forceinline__ bool overlaps(const float4 box, int L, int T, int R, int B) {
-    return box.x < (float)R && box.z > (float)L && box.y < (float)B && box.w > (float)T;
-}
-
+// fact (1) above, with the reference's float compares (TileTree.hs:120-139).  The tree only ever tests a box
+// against a cut, never against the outside edge of the square it covers, so a root tile in the first / last
+// column or row takes everything on that side: for the culled, consistent boxes the ABI asks for that is no
+// different from a plain overlap test, and for anything else (inverted or NaN boxes, shapes off the canvas)
+// it is what addShapeToTree does with them.
 template <class F>
 __device__ __forceinline__ void forEachRoot(const BinParams& P, const float4 box, F&& f) {
     const int R = P.rootsPerSide, S = P.rootSize;
     // candidate range, one root to spare on each side; clamped as floats, because a box may be far outside
-    // what an int holds (or infinite) and `overlaps`, like the reference, compares floats
+    // what an int holds (or infinite)
     const float last = (float)(R - 1);
-    const int tx0 = (int)fminf(fmaxf(floorf(box.x / (float)S) - 1.0f, 0.0f), last + 1.0f);
-    const int tx1 = (int)fmaxf(fminf(floorf(box.z / (float)S) + 1.0f, last), -1.0f);
-    const int ty0 = (int)fminf(fmaxf(floorf(box.y / (float)S) - 1.0f, 0.0f), last + 1.0f);
-    const int ty1 = (int)fmaxf(fminf(floorf(box.w / (float)S) + 1.0f, last), -1.0f);
+    const int tx0 = (int)fminf(fmaxf(floorf(box.x / (float)S) - 1.0f, 0.0f), last);
+    const int tx1 = (int)fmaxf(fminf(floorf(box.z / (float)S) + 1.0f, last), 0.0f);
+    const int ty0 = (int)fminf(fmaxf(floorf(box.y / (float)S) - 1.0f, 0.0f), last);
+    const int ty1 = (int)fmaxf(fminf(floorf(box.w / (float)S) + 1.0f, last), 0.0f);
     for (int ty = ty0; ty <= ty1; ty++) {
         if (!rootActive(P, ty)) continue;
+        if (!((ty == R - 1 || box.y < (float)((ty + 1) * S)) && (ty == 0 || box.w > (float)(ty * S)))) continue;
         for (int tx = tx0; tx <= tx1; tx++)
-            if (overlaps(box, tx * S, ty * S, (tx + 1) * S, (ty + 1) * S)) f(mortonYX(tx, ty));
+            if ((tx == R - 1 || box.x < (float)((tx + 1) * S)) && (tx == 0 || box.z > (float)(tx * S))) f(mortonYX(tx, ty));
     }
 }
 

@@ -245,6 +245,20 @@ def test_boxes_beyond_int32_are_binned(emu_scene, level):
         run_scene(emu_scene, scenes.far_shapes(12, 150, 110, 0xFA50 + seed), level)
 
 
+@pytest.mark.parametrize("field", ["left", "top", "right", "bottom"])
+def test_boxes_that_break_the_contract_are_binned_as_the_tile_tree_would(emu_scene, field):
+    """Level 2 asks for culled, consistent boxes.  Given others — a side turned into NaN, +-inf or +-1e30, so that the
+    box is inverted or off the canvas — addShapeToTree (TileTree.hs:120-139) still does something definite: it tests
+    the box against cuts only, so the first / last row or column of root tiles takes what lies beyond it.  The binning
+    kernels do the same (tiles, shape lists, counts and pixels equal the oracle's)."""
+    for value in (np.nan, np.inf, -np.inf, 1e30, -1e30):
+        scene = scenes.fuzzy_circles(30, 300, 280, 5, 40, 11)      # 2 x 2 root tiles of 256 pixels
+        scene.entries = scene.entries.copy()
+        scene.entries[field][3] = value
+        scene.entries[field][17] = value
+        run_scene(emu_scene, scene, 2)
+
+
 @pytest.mark.parametrize("level", [2, 3])
 def test_infinite_coordinate_is_refused_at_levels_2_and_3(emu_scene, level):
     """Level 2: the poisoned heap arrives with finite boxes.  Level 3: the outline itself holds the infinite point; the
