@@ -56,6 +56,18 @@ SCENES = {
 }
 VERBATIM = ("tiny_square", "medium_square", "open_square", "hour_glass", "translucent_stack")
 
+# BASELINE.json's configs at their stated sizes (reference_hashes_fullsize.json, `--fullsize`): minutes of CPU
+# time, so they are kept apart from the quick set above.  The -m gpu tests hold the CUDA path to them at
+# levels 1 and 2 (tests/test_gpu_fullsize.py).
+FULLSIZE = {
+    "s2_1920x1080": (lambda: scenes.s2(1920, 1080), None),
+    "s3_3840x2160": (lambda: scenes.s3(3840, 2160), None),
+    "s4b_3840x2160": (scenes.s4b, None),
+    "s4_3840x2160": (scenes.s4, None),
+    "s5_16384": (scenes.s5, None),
+    "s5b_16384": (scenes.s5b, None),
+}
+
 
 def digest(result):
     counts = np.concatenate(result.n_thresholds).astype("<i4")
@@ -68,7 +80,7 @@ def digest(result):
 
 def render(name, reference):
     from oracle import oracle
-    make, spec = SCENES[name]
+    make, spec = SCENES[name] if name in SCENES else FULLSIZE[name]
     kw = {} if spec is None else {"spec": spec}
     return oracle.render(make(), reference=reference, **kw)
 
@@ -77,6 +89,21 @@ if __name__ == "__main__":
     from oracle import oracle
     if oracle.reference_lib() is None:
         sys.exit("needs the reference tree (/root/reference) to compile its kernels")
+    if "--fullsize" in sys.argv:
+        out = {}
+        for name in FULLSIZE:
+            r = render(name, reference=True)
+            assert r.overflow_threads == 0, name
+            out[name] = digest(r)
+            out[name]["canvas"] = [int(r.image.shape[1]), int(r.image.shape[0])]
+            # the restated oracle on the same jobs: the two must agree before anything is written
+            mine = digest(render(name, reference=False))
+            assert all(mine[k] == out[name][k] for k in mine), (name, mine, out[name])
+            print(name, json.dumps(out[name]), flush=True)
+            del r
+        with open(os.path.join(HERE, "reference_hashes_fullsize.json"), "w") as f:
+            json.dump(out, f, indent=1, sort_keys=True)
+        sys.exit(0)
     out, images = {}, {}
     for name in SCENES:
         r = render(name, reference=True)

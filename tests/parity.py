@@ -16,6 +16,8 @@ def channel_diff(a, b):
 
 def assert_images_match(gpu, ref, exact=False):
     assert gpu.shape == ref.shape
+    if np.array_equal(gpu, ref):   # the usual case; spares the int32 temporaries on a 16384^2 canvas
+        return
     d = channel_diff(gpu, ref)
     if exact:
         bad = np.argwhere(d > 0)
