@@ -61,7 +61,18 @@ struct gudni_ctx {
     DevBuf strandBounds;                     // per-strand y range, geometry_bytes / 16 entries
     unsigned long long storeCap = 0;
     unsigned long long storeDemand = 0;   // thresholds the generate kernel wanted to store last frame
+    DevBuf streamPool;                    // slice -> colour hand-over: section streams, 128-byte chunks
+    unsigned long long streamCapChunks = 0;
+    unsigned long long streamDemand = 0;  // chunks the slice kernel drew last frame
+    // resident CTAs per SM of the persistent kernels on this context's device
+    bool occupancyKnown = false;
+    int genCtasPerSm = 0, sweepCtasPerSm = 0, sliceCtasPerSm = 0, colorCtasPerSm = 0, numSms = 0;
+    int resolveCtasPerSm = 0, compositeCtasPerSm = 0, accumulateCtasPerSm = 0;
+    DevBuf stackKeys, stackColors, refSlabs;   // the frame's table of distinct shape stacks
+    unsigned long long refCapSlabs = 0;
+    unsigned long long refDemand = 0;          // slabs of stack numbers drawn last frame
     int spillSlots = 0;
+    int64_t retriedFrames = 0;            // frames rasterized twice because a per-frame buffer was undersized
 
     // taps
     bool debug = false;

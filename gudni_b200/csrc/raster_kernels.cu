@@ -4,7 +4,7 @@
 
 #include <algorithm>
 
-#include "raster_warp.cuh"
+#include "raster_split.cuh"
 
 using namespace gudni_dev;
 
@@ -14,8 +14,19 @@ using namespace gudni_dev;
 #ifndef GUDNI_SWEEP_WARPS
 #define GUDNI_SWEEP_WARPS 2
 #endif
+#ifndef GUDNI_SLICE_WARPS
+#define GUDNI_SLICE_WARPS 4
+#endif
+#ifndef GUDNI_COLOR_WARPS
+#define GUDNI_COLOR_WARPS 4
+#endif
+#ifndef GUDNI_SPLIT_SWEEP
+#define GUDNI_SPLIT_SWEEP 1     // 1: raster_slice_kernel + raster_color_kernel; 0: round 1's raster_sweep_kernel
+#endif
 constexpr int kGenWarpsPerCta = GUDNI_GEN_WARPS;
 constexpr int kSweepWarpsPerCta = GUDNI_SWEEP_WARPS;
+constexpr int kSliceWarpsPerCta = GUDNI_SLICE_WARPS;
+constexpr int kColorWarpsPerCta = GUDNI_COLOR_WARPS;
 
 // The frame is rasterized by two persistent kernels.  Both size their grid to what the chip holds
 // resident and every warp pulls (tile, 32-column group) units from a global counter until the frame
@@ -61,8 +72,9 @@ __global__ void __launch_bounds__(kGenWarpsPerCta * 32, GUDNI_GEN_MIN_CTAS) rast
         const gudni_tile tile = P.tiles[tileIndex];
         int generated = -1;
         int failed = 0;
+        bool exhausted = false;
         if (tile.shape_count <= denseCap) {
-            failed = generateWarp(P, q, tile, tileIndex, recUnit, column, generated);
+            failed = generateWarp(P, q, tile, tileIndex, recUnit, column, generated, exhausted);
         } else {
             // a tile that stopped splitting at the 8-pixel floor with more shapes than stack bits:
             // its threads take the lane-private replay path (bit -> shape table, HBM queue)
@@ -76,6 +88,7 @@ __global__ void __launch_bounds__(kGenWarpsPerCta * 32, GUDNI_GEN_MIN_CTAS) rast
         unsigned int mine = (!failed && generated > 0) ? (unsigned)generated : 0u;
         for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(full, mine, d);
         if (lane == 0 && mine) atomicAdd(&P.counters[kCntThresholds], (unsigned long long)mine);
+        if (exhausted) atomicAdd(&P.counters[kCntExhausted], 1ull);
         if (failed) registerSpill(P, tileIndex, column);
     }
 }
@@ -123,6 +136,142 @@ __global__ void __launch_bounds__(kSweepWarpsPerCta * 32, GUDNI_SWEEP_MIN_CTAS) 
     }
 }
 
+// The sweep's state machine alone (raster_split.cuh): sorted thresholds in, section streams out.
+#ifndef GUDNI_SLICE_MIN_CTAS
+#define GUDNI_SLICE_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(kSliceWarpsPerCta * 32, GUDNI_SLICE_MIN_CTAS) raster_slice_kernel(const FrameParams P, int tileBase, int nTiles) {
+    __shared__ SliceScratch scratch[kSliceWarpsPerCta];
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SliceScratch& W = scratch[warp];
+    if (lane == 0) { W.slabNext = 0u; W.slabEnd = 0u; }
+    __syncwarp();
+    LaneQueue q;
+    q.limit = min(kQueueCap, P.maxThresholds);
+    q.thrHot = W.qThr + lane;
+    q.hdrHot = W.qHdr + lane;
+    const int warpShift = P.computeDepth - 5;
+    const unsigned totalUnits = (unsigned)nTiles << warpShift;
+    const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
+    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkSweep);
+    for (;;) {
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd(workCounter, 1u);
+        unit = __shfl_sync(full, unit, 0);
+        if (unit >= totalUnits) break;
+        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> warpShift)];
+        const unsigned warpInTile = unit & ((1u << warpShift) - 1u);
+        const int column = (int)(warpInTile << 5) + lane;
+        const unsigned recUnit = ((unsigned)tileIndex << warpShift) + warpInTile;
+        const gudni_tile tile = P.tiles[tileIndex];
+        if (tile.shape_count > denseCap) continue;   // replayed lane-privately
+        const unsigned int count = P.threadRecs[(size_t)recUnit * 32 + lane].count;
+        bool exhausted = false;
+        const int failed = sliceWarp(P, W, q, tile, recUnit, column, exhausted);
+        if (failed) {
+            // its thresholds were counted by the generate kernel; the replay counts them again
+            atomicAdd(&P.counters[kCntThresholds], 0ull - (unsigned long long)count);
+            if (exhausted) atomicAdd(&P.counters[kCntExhausted], 1ull);
+            registerSpill(P, tileIndex, column);
+        }
+    }
+}
+
+// Persistent-warp loop over the (tile, 32-column group) units of a launch, most expensive tiles first.
+// body(tileIndex, tile, recUnit, column) is called by the whole warp for every unit of a dense tile.
+template <class F>
+__device__ __forceinline__ void forEachUnit(const FrameParams& P, int tileBase, int nTiles, int counterSlot, F body) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warpShift = P.computeDepth - 5;
+    const unsigned totalUnits = (unsigned)nTiles << warpShift;
+    const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
+    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + counterSlot);
+    for (;;) {
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd(workCounter, 1u);
+        unit = __shfl_sync(full, unit, 0);
+        if (unit >= totalUnits) break;
+        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> warpShift)];
+        const unsigned warpInTile = unit & ((1u << warpShift) - 1u);
+        const gudni_tile tile = P.tiles[tileIndex];
+        if (tile.shape_count > denseCap) continue;   // replayed lane-privately
+        body(tileIndex, tile, ((unsigned)tileIndex << warpShift) + warpInTile, (int)(warpInTile << 5) + lane);
+    }
+}
+
+#ifndef GUDNI_RESOLVE_WARPS
+#define GUDNI_RESOLVE_WARPS 4
+#endif
+#ifndef GUDNI_COMPOSITE_WARPS
+#define GUDNI_COMPOSITE_WARPS 4
+#endif
+#ifndef GUDNI_ACCUMULATE_WARPS
+#define GUDNI_ACCUMULATE_WARPS 4
+#endif
+constexpr int kResolveWarpsPerCta = GUDNI_RESOLVE_WARPS;
+constexpr int kCompositeWarpsPerCta = GUDNI_COMPOSITE_WARPS;
+constexpr int kAccumulateWarpsPerCta = GUDNI_ACCUMULATE_WARPS;
+
+// Section streams -> numbered shape stacks (raster_split.cuh).
+__global__ void __launch_bounds__(kResolveWarpsPerCta * 32) raster_resolve_kernel(const FrameParams P, int tileBase, int nTiles) {
+    __shared__ ResolveScratch scratch[kResolveWarpsPerCta];
+    ResolveScratch& W = scratch[threadIdx.x >> 5];
+    RefSlab slab{kRefNone, 0u, -1};
+    forEachUnit(P, tileBase, nTiles, kCntWorkResolve, [&](int tileIndex, const gudni_tile& tile, unsigned recUnit, int column) {
+        if (tileHasPictures(P, tile)) return;   // raster_picture_kernel
+        const unsigned int count = P.threadRecs[(size_t)recUnit * 32 + (threadIdx.x & 31)].count;
+        if (resolveWarp(P, W, slab, tileIndex, recUnit)) {
+            atomicAdd(&P.counters[kCntThresholds], 0ull - (unsigned long long)count);
+            atomicAdd(&P.counters[kCntExhausted], 1ull);
+            registerSpill(P, tileIndex, column);
+        }
+    });
+    closeSlab(P, slab);
+}
+
+// Every numbered stack composited once: a warp per slab of numbers.
+__global__ void __launch_bounds__(kCompositeWarpsPerCta * 32) raster_composite_kernel(const FrameParams P) {
+    __shared__ TileTable tables[kCompositeWarpsPerCta];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    TileTable& T = tables[threadIdx.x >> 5];
+    const unsigned int nSlabs = (unsigned int)min(P.counters[kCntRefSlabs], (unsigned long long)P.refCapSlabs);
+    const unsigned int firstSlab = (unsigned int)P.counters[kCntCompositeBase];
+    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkComposite);
+    int tableTile = -1;
+    bool tame = false;
+    for (;;) {
+        unsigned int s = 0;
+        if (lane == 0) s = firstSlab + atomicAdd(workCounter, 1u);
+        s = __shfl_sync(full, s, 0);
+        if (s >= nSlabs) break;
+        compositeSlab(P, T, tableTile, tame, s);
+    }
+}
+
+// The resolved streams with the colours at hand: accumulation and pixel stores.
+__global__ void __launch_bounds__(kAccumulateWarpsPerCta * 32) raster_accumulate_kernel(const FrameParams P, int tileBase, int nTiles) {
+    forEachUnit(P, tileBase, nTiles, kCntWorkAccumulate, [&](int, const gudni_tile& tile, unsigned recUnit, int column) {
+        if (tileHasPictures(P, tile)) return;
+        accumulateWarp(P, tile, recUnit, column);
+    });
+}
+
+// Tiles with picture substances: one pass, every lane composites its own sections (the colour depends on the pixel).
+__global__ void __launch_bounds__(kColorWarpsPerCta * 32) raster_picture_kernel(const FrameParams P, int tileBase, int nTiles) {
+    __shared__ TileTable tables[kColorWarpsPerCta];
+    TileTable& T = tables[threadIdx.x >> 5];
+    forEachUnit(P, tileBase, nTiles, kCntWorkColor, [&](int, const gudni_tile& tile, unsigned recUnit, int column) {
+        __syncwarp();
+        bool anyPicture, anyWild;
+        buildTileTable(P, T, tile, anyPicture, anyWild);
+        __syncwarp();
+        if (anyPicture) pictureWarp(P, T, tile, recUnit, column);
+    });
+}
+
 // Replay of spilled column-threads.  Persistent: each thread owns one HBM queue slot and walks the
 // spill list with a grid stride, so the scratch footprint is fixed (slots x MAXTHRESHOLDS x 20 B)
 // regardless of how many threads spilled.
@@ -154,9 +303,11 @@ __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, 
 // strand_bounds_kernel earlier on the stream): the tiles of the launch lose their shape lists, so the
 // raster kernels that follow never walk a strand and only paint background; frame_end reports the error.
 __global__ void __launch_bounds__(1024) tile_order_kernel(gudni_tile* __restrict__ tiles, int tileBase, int nTiles,
-                                                          uint32_t* __restrict__ order, const unsigned long long* __restrict__ counters) {
+                                                          uint32_t* __restrict__ order, unsigned long long* __restrict__ counters) {
     __shared__ unsigned int bins[256];
     __shared__ unsigned int starts[256];
+    // the stack table runs on across the launches of a frame: this launch's composite pass starts where the table stands now
+    if (threadIdx.x == 0) counters[kCntCompositeBase] = counters[kCntRefSlabs];
     if (counters[kCntNonFinite])
         for (int i = threadIdx.x; i < nTiles; i += blockDim.x) tiles[tileBase + i].shape_count = 0u;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) bins[i] = 0u;
@@ -251,30 +402,61 @@ int selftestDiv3(gudni_ctx* ctx, unsigned long long n, unsigned long long seed, 
 int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTiles) {
     if (nTiles <= 0) return GUDNI_OK;
     FrameParams P = frame;
-    static int genCtasPerSm = 0, sweepCtasPerSm = 0, numSms = 0;
+    // occupancy of the persistent kernels on THIS context's device (a process may hold several contexts)
     const size_t sweepSmem = kSweepWarpsPerCta * sizeof(WarpScratch);
-    if (!genCtasPerSm) {
+    if (!ctx->occupancyKnown) {
         GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweepSmem));
-        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sweepCtasPerSm, raster_sweep_kernel,
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sweepCtasPerSm, raster_sweep_kernel,
                                                                           kSweepWarpsPerCta * 32, sweepSmem));
-        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&genCtasPerSm, raster_generate_kernel,
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->genCtasPerSm, raster_generate_kernel,
                                                                           kGenWarpsPerCta * 32, 0));
-        GUDNI_CUDA_TRY(ctx, cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, ctx->device));
-        if (genCtasPerSm < 1) genCtasPerSm = 1;
-        if (sweepCtasPerSm < 1) sweepCtasPerSm = 1;
+        GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_slice_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sliceCtasPerSm, raster_slice_kernel,
+                                                                          kSliceWarpsPerCta * 32, 0));
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->colorCtasPerSm, raster_picture_kernel,
+                                                                          kColorWarpsPerCta * 32, 0));
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resolveCtasPerSm, raster_resolve_kernel,
+                                                                          kResolveWarpsPerCta * 32, 0));
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->compositeCtasPerSm, raster_composite_kernel,
+                                                                          kCompositeWarpsPerCta * 32, 0));
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->accumulateCtasPerSm, raster_accumulate_kernel,
+                                                                          kAccumulateWarpsPerCta * 32, 0));
+        ctx->resolveCtasPerSm = std::max(ctx->resolveCtasPerSm, 1);
+        ctx->compositeCtasPerSm = std::max(ctx->compositeCtasPerSm, 1);
+        ctx->accumulateCtasPerSm = std::max(ctx->accumulateCtasPerSm, 1);
+        GUDNI_CUDA_TRY(ctx, cudaDeviceGetAttribute(&ctx->numSms, cudaDevAttrMultiProcessorCount, ctx->device));
+        ctx->genCtasPerSm = std::max(ctx->genCtasPerSm, 1);
+        ctx->sweepCtasPerSm = std::max(ctx->sweepCtasPerSm, 1);
+        ctx->sliceCtasPerSm = std::max(ctx->sliceCtasPerSm, 1);
+        ctx->colorCtasPerSm = std::max(ctx->colorCtasPerSm, 1);
+        ctx->occupancyKnown = true;
     }
+    const int numSms = ctx->numSms;
     P.numStreams = std::max(1, std::min(std::min(numSms, gudni_dev::kMaxSms), nTiles));
-    // work counters of the two kernels (the threshold store cursor runs on across the jobs of a frame)
+    // work counters of the kernels (the threshold store and stream cursors run on across the jobs of a frame)
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 32, 0, gudni_dev::kMaxSms * sizeof(unsigned int), ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkSweep, 0, 8, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkColor, 0, 8, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkResolve, 0, 24, ctx->stream));
     const long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
-    const int genGrid = (int)std::min<long long>((long long)genCtasPerSm * numSms, (units + kGenWarpsPerCta - 1) / kGenWarpsPerCta);
-    const int sweepGrid = (int)std::min<long long>((long long)sweepCtasPerSm * numSms, (units + kSweepWarpsPerCta - 1) / kSweepWarpsPerCta);
+    auto grid = [&](int ctasPerSm, int warpsPerCta) {
+        return (int)std::min<long long>((long long)ctasPerSm * numSms, (units + warpsPerCta - 1) / warpsPerCta);
+    };
     tile_order_kernel<<<1, 1024, 0, ctx->stream>>>(const_cast<gudni_tile*>(P.tiles), tileBase, nTiles, const_cast<uint32_t*>(P.tileOrder), P.counters);
     ctx->launches++;
-    raster_generate_kernel<<<genGrid, kGenWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
-    raster_sweep_kernel<<<sweepGrid, kSweepWarpsPerCta * 32, sweepSmem, ctx->stream>>>(P, tileBase, nTiles);
-    ctx->launches += 2;
+    raster_generate_kernel<<<grid(ctx->genCtasPerSm, kGenWarpsPerCta), kGenWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
+    ctx->launches++;
+#if GUDNI_SPLIT_SWEEP
+    raster_slice_kernel<<<grid(ctx->sliceCtasPerSm, kSliceWarpsPerCta), kSliceWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
+    raster_resolve_kernel<<<grid(ctx->resolveCtasPerSm, kResolveWarpsPerCta), kResolveWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
+    raster_composite_kernel<<<ctx->compositeCtasPerSm * numSms, kCompositeWarpsPerCta * 32, 0, ctx->stream>>>(P);
+    raster_accumulate_kernel<<<grid(ctx->accumulateCtasPerSm, kAccumulateWarpsPerCta), kAccumulateWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
+    raster_picture_kernel<<<grid(ctx->colorCtasPerSm, kColorWarpsPerCta), kColorWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
+    ctx->launches += 5;
+#else
+    raster_sweep_kernel<<<grid(ctx->sweepCtasPerSm, kSweepWarpsPerCta), kSweepWarpsPerCta * 32, sweepSmem, ctx->stream>>>(P, tileBase, nTiles);
+    ctx->launches++;
+#endif
     GUDNI_CUDA_TRY(ctx, cudaGetLastError());
     return GUDNI_OK;
 }

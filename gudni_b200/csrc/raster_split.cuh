@@ -1,0 +1,596 @@
+// raster_split.cuh — renderThresholds (Kernels.cl:2117-2167) as two kernels with a section stream between them.
+//
+// The reference's render phase does two very different things per column-thread: a branchy, sequential walk
+// down the sorted threshold queue that cuts the column into bands and sections (verticalAdvance /
+// horizontalAdvance / sliceActive, K.cl:1007-1077, 1744-1851), and for every section a walk down the shape
+// stack compositing translucent layers (determineColor, K.cl:1447-1513).  The first is integer / queue work in
+// which neighbouring lanes rarely agree on the branch; the second is a long dependent fp32 chain that is the
+// same code in every lane.  Run in one kernel they share one register budget and one shared-memory budget
+// (12 warps per SM in round 1) and the divergent half drags the colour state through every branch.
+//
+//   raster_slice_kernel   one lane per column-thread: the sweep's state machine only.  No shape stack, no
+//                         colour: it never needs to know WHICH shapes are present to decide where bands and
+//                         sections lie.  Emits the column's *section stream*: 8-byte records
+//                           SEC  (toggle bit | first-of-band, area)   one section; afterwards the bit flips
+//                           FLIP (bit)                                a persistent threshold crossing a band border
+//                           PEND (n)                                  pixel complete; store it n times (runs of untouched rows)
+//                           LINK (next chunk) / END
+//                         into a chain of 128-byte chunks (16 records, the last one the link) drawn from one pool.
+//   raster_resolve_kernel / raster_composite_kernel / raster_accumulate_kernel
+//                         replay the streams: number the distinct shape stacks, composite each once, add
+//                         colour * area per section and store the pixels (see "colours" below).
+//
+// Every lane still adds colour * area into its own accumulators in section order (K.cl:1904), so pixels are
+// bit-identical to the reference.
+#pragma once
+#include "raster_warp.cuh"
+
+namespace gudni_dev {
+
+// ---- the section stream ---------------------------------------------------------------------------------------
+constexpr int kChunkRecs = 16;                     // 128 bytes: one L2 line
+constexpr uint32_t kRecKindMask = 0xC0000000u;
+constexpr uint32_t kRecSection = 0x00000000u;      // .x = kind | first | bit, .y = area (f32 bits)
+constexpr uint32_t kRecFlip = 0x40000000u;         // .x = kind | bit
+constexpr uint32_t kRecPixelEnd = 0x80000000u;     // .x = kind | repeat count
+constexpr uint32_t kRecLink = 0xC0000000u;         // .y = next chunk, kStreamEnd: the stream ends here
+constexpr uint32_t kRecFirst = 0x00000100u;        // SEC: first section of its band
+constexpr uint32_t kRecBitMask = 0x000000FFu;
+constexpr uint32_t kRecNoBit = 0x000000FFu;        // SEC without a threshold behind it (the band's last section)
+constexpr uint32_t kStreamEnd = 0xFFFFFFFFu;
+constexpr int kMaxPixelRun = 0xFFFF;
+
+#ifndef GUDNI_SLAB_CHUNKS
+#define GUDNI_SLAB_CHUNKS 128
+#endif
+constexpr unsigned int kSlabChunks = GUDNI_SLAB_CHUNKS;   // chunks a warp draws from the pool at a time
+constexpr unsigned int kSlabLow = 40;                      // refill when fewer are left at the top of a round
+
+struct SliceScratch {
+    float4 qThr[kQueueHot * 32];     // head window of the 32 threshold queues
+    uint32_t qHdr[kQueueHot * 32];
+    unsigned int slabNext, slabEnd;  // the warp's private range of pool chunks
+    unsigned int pad[2];
+};
+
+// Warp-converged: make sure the warp's slab holds at least `want` chunks (a lane that still runs dry inside a
+// round falls back to the global cursor).  What is left of the old slab is abandoned: address space, not traffic.
+__device__ __forceinline__ void ensureSlab(const FrameParams& P, SliceScratch& W, unsigned int want) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned int next = W.slabNext, end = W.slabEnd;
+        if (next >= end || end - next < want) {
+            const unsigned int b = (unsigned int)atomicAdd(&P.counters[kCntStreamCursor], (unsigned long long)kSlabChunks);
+            W.slabNext = b;
+            W.slabEnd = b + kSlabChunks;
+        }
+    }
+    __syncwarp();
+}
+
+struct StreamWriter {
+    uint2* chunk;
+    int pos;
+    bool failed;           // the pool ran out
+    unsigned int first;    // first chunk of the stream
+    __device__ __forceinline__ unsigned int alloc(const FrameParams& P, SliceScratch& W) {
+        unsigned int c = atomicAdd(&W.slabNext, 1u);
+        if (c >= W.slabEnd) c = (unsigned int)atomicAdd(&P.counters[kCntStreamCursor], 1ull);
+        return c;
+    }
+    __device__ __forceinline__ void open(const FrameParams& P, SliceScratch& W) {
+        failed = false;
+        pos = 0;
+        first = alloc(P, W);
+        if (first >= P.streamCapChunks) { failed = true; first = 0u; }
+        chunk = P.streamPool + (size_t)first * kChunkRecs;
+    }
+    __device__ __forceinline__ void put(const FrameParams& P, SliceScratch& W, uint32_t tag, uint32_t payload) {
+        if (failed) return;
+        if (pos == kChunkRecs - 1) {   // the last slot of a chunk links to the next one
+            const unsigned int c = alloc(P, W);
+            if (c >= P.streamCapChunks) { failed = true; return; }
+            chunk[pos] = make_uint2(kRecLink, c);
+            chunk = P.streamPool + (size_t)c * kChunkRecs;
+            pos = 0;
+        }
+        chunk[pos++] = make_uint2(tag, payload);
+    }
+    __device__ __forceinline__ void close() {
+        if (!failed) chunk[pos] = make_uint2(kRecLink, kStreamEnd);   // pos <= kChunkRecs - 1 always
+    }
+};
+
+// verticalAdvance, K.cl:1744-1824, without the shape stack: what it does to the stack (toggling the persistent
+// thresholds that cross the band border) goes into the stream as FLIP records; the un-toggling of the band that
+// ended (K.cl:1756-1759) is the resolve kernel resetting `cur` at the next first-of-band section.
+template <class Q>
+__device__ __forceinline__ void sliceVertical(const FrameParams& P, SliceScratch& W, StreamWriter& out, Q& q, SweepState& st,
+                                              float floatHeight) {
+    st.gapTop = 0.0f;
+    const float nextBreak = fminf(floatHeight, st.pixelY);
+    const float activeBottom = q.len > 0 ? q.getT(0).bottom : FLT_MAX;
+    if (activeBottom == st.ey) {   // the active run ends here: its persistent bottoms toggle, then it is popped
+        for (int i = 0; i < st.numActive; i++) {
+            const uint32_t h = q.getH(i);
+            if (hPersistBottom(h)) out.put(P, W, kRecFlip | (h & kRecBitMask), 0u);
+        }
+        q.popN(st.numActive);
+        st.numActive = 0;
+    }
+    float nextBottom;
+    if (st.numActive > 0) {
+        nextBottom = fminf(activeBottom, nextBreak);
+    } else {
+        const float nextTop = q.len > 0 ? q.getT(0).top : FLT_MAX;
+        if (nextTop > st.ey) {
+            nextBottom = fminf(nextBreak, nextTop);
+            st.gapTop = nextTop;   // nothing crosses the column above this y
+        } else {
+            float activeTop;
+            nextBottom = fminf(nextBreak, splitNext(q, st.numActive, activeTop));
+            while (st.numActive > 0) {
+                const Thr t0 = q.getT(0);
+                if (t0.top != t0.bottom) break;
+                const uint32_t h = q.getH(0);
+                if (hPersistTop(h)) out.put(P, W, kRecFlip | (h & kRecBitMask), 0u);
+                q.pop();
+                st.numActive--;
+            }
+            // K.cl:1803-1808 tests tTop(threshold i) > RENDERSTART per active; the actives share their top
+            if (activeTop > 0.0f) {
+                for (int i = 0; i < st.numActive; i++) {
+                    const uint32_t h = q.getH(i);
+                    if (hPersistTop(h)) out.put(P, W, kRecFlip | (h & kRecBitMask), 0u);
+                }
+            }
+        }
+    }
+    st.sy = st.ey;
+    st.ey = nextBottom;
+    st.sx = st.ex = 0.0f;
+    st.cur = 0;
+}
+
+// ---- slice kernel body -------------------------------------------------------------------------------------------
+// One warp, one (tile, 32-column group) of a dense tile.  Returns per lane 1 if the thread has to be replayed
+// (its queue outgrew the on-chip capacity while slicing, or the stream pool ran out: `exhausted`).
+__device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, LaneQueue& q, const gudni_tile& tile,
+                                         unsigned unit, int column, bool& exhausted) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const ThreadGeom g = threadGeom(P, tile, column);
+    // a picture's colour depends on the row, so runs of untouched rows are only folded in tiles without pictures
+    bool anyPicture = false;
+    for (uint32_t i = lane; i < tile.shape_count; i += 32)
+        anyPicture = anyPicture || (tagMeta(__ldg(&P.shapes[tile.shape_start + i].tag)) & kMetaPicture);
+    const bool foldable = !__any_sync(full, anyPicture);
+    ThreadRec* recp = P.threadRecs + (size_t)unit * 32 + lane;
+    const unsigned int recOffset = recp->offset, recCount = recp->count;
+    const bool mine = recCount != kRecInactive;
+    const float floatHeight = (float)g.intHeight;
+    SweepState st;
+    st.alive = false;
+    q.init();
+    ensureSlab(P, W, 32u + kSlabLow);
+    StreamWriter out;
+    out.failed = false; out.pos = 0; out.first = 0u; out.chunk = P.streamPool;
+    if (mine) {
+        q.attach(P.thrStore, P.hdrStore, recOffset, (int)recCount, kStoreSlack);
+        st.init(floatHeight);
+        out.open(P, W);
+    }
+    bool spilled = false;
+    bool first = false;    // the next section record opens a band
+    int blankRun = 1;      // pixels the band being swept stands for
+    for (;;) {
+        if (!__any_sync(full, st.alive)) break;
+        ensureSlab(P, W, kSlabLow);
+        // ---- band boundary: close the pixel, open the next band (see sweepWarp (A) for the blank-run shortcut)
+        if (st.alive && st.ex == 1.0f) {
+            if (st.ey >= st.pixelY) {   // calculatePixel's loop condition failed: the pixel is complete
+                out.put(P, W, kRecPixelEnd | (uint32_t)blankRun, 0u);
+                nextPixel(st, floatHeight);
+                if (blankRun > 1) {
+                    const float skipped = (float)(blankRun - 1);
+                    st.sy += skipped;
+                    st.ey = st.sy;
+                    st.pixelY += skipped;
+                    st.row += blankRun - 1;
+                    st.alive = st.pixelY <= floatHeight;
+                }
+            }
+            if (st.alive) {
+                sliceVertical(P, W, out, q, st, floatHeight);
+                if (q.failed()) { spilled = true; st.alive = false; }
+                first = true;
+                blankRun = 1;
+                if (foldable && st.sy == st.pixelY - 1.0f) {
+                    const float limit = fminf(st.gapTop, floatHeight);
+                    if (limit >= st.pixelY + 1.0f) blankRun = min((int)(limit - st.pixelY) + 1, kMaxPixelRun);
+                }
+            }
+        }
+        // ---- the sections of the band: horizontalAdvance (K.cl:1826-1851) + the bookkeeping of calculatePixel
+        while (st.alive) {
+            float nextX = 1.0f;
+            uint32_t bit = kRecNoBit;
+            if (st.cur < st.numActive) {
+                const Thr t = q.getT(st.cur);
+                const uint32_t h = q.getH(st.cur);
+                const float yMid = st.sy + ((st.ey - st.sy) * 0.5f);
+                const float x = intersectX(h, t, yMid);
+                nextX = (x >= 1.0f) ? 0.0f : fmaxf(0.0f, x);
+                bit = h & kRecBitMask;
+            }
+            st.sx = st.ex;
+            st.ex = nextX;
+            const float area = (st.ex - st.sx) * (st.ey - st.sy);
+            st.cur++;
+            // a zero-area section adds colour * 0 = 0 to every accumulator: it only matters for its toggle
+            if (area != 0.0f || bit != kRecNoBit || first) {
+                out.put(P, W, kRecSection | (first ? kRecFirst : 0u) | bit, __float_as_uint(area));
+                first = false;
+            }
+            if (st.ex == 1.0f) break;
+        }
+        if (out.failed) st.alive = false;
+    }
+    exhausted = false;
+    if (mine) {
+        out.close();
+        if (out.failed) { spilled = true; exhausted = true; }
+        recp->chunk = out.first;
+        if (spilled) recp->count = kRecInactive;   // the later passes skip it; the replay renders the whole thread
+    }
+    return spilled ? 1 : 0;
+}
+
+// ---- colours: resolve -> composite -> accumulate ------------------------------------------------------------
+// The section streams are replayed twice.  raster_resolve_kernel rebuilds the shape stack of every section from
+// the toggles and gives every *distinct* stack a number (a per-warp cache in shared memory keyed by the 128-bit
+// stack does the deduplication: neighbouring columns and rows keep meeting the same few stacks); the stack goes
+// into a global table, its number into the section's record.  raster_composite_kernel then composites every
+// stack of the table once — one stack per lane, every lane of every warp busy with the same loop, operation for
+// operation determineColor (K.cl:1447-1513).  raster_accumulate_kernel walks the streams again and adds
+// colour * area into the pixel's accumulators in section order (K.cl:1904) and stores the pixels.
+// Stack numbers are handed out in slabs of kRefSlab owned by one warp while it works on one tile, so all
+// stacks of a slab share the tile's substance table and the composite kernel builds it once per slab.
+// Tiles with picture substances (the colour depends on the pixel, K.cl:1420-1441) take raster_picture_kernel
+// instead: one pass, every lane composites its own sections.
+#ifndef GUDNI_COLOR_LINES
+#define GUDNI_COLOR_LINES 256
+#endif
+constexpr int kColorLines = GUDNI_COLOR_LINES;     // per-warp stack cache of the resolve kernel (power of two)
+#ifndef GUDNI_REF_SLAB
+#define GUDNI_REF_SLAB 128
+#endif
+constexpr unsigned int kRefSlab = GUDNI_REF_SLAB;  // stack numbers a warp draws at a time
+constexpr uint32_t kRefNone = 0xFFFFFFFFu;
+constexpr uint32_t kRefMask = 0x3FFFFFFFu;         // a SEC record's first word once resolved (kind bits stay 00)
+
+struct ResolveScratch {
+    ulonglong2 key[kColorLines];     // stack (lo, hi)
+    uint32_t ref[kColorLines];       // its number; kRefNone: empty line
+    uint8_t claim[kColorLines];
+};
+
+__device__ __forceinline__ void colorLines(uint64_t hi, uint64_t lo, uint32_t& line1, uint32_t& line2) {
+    uint32_t t = (uint32_t)lo ^ ((uint32_t)(lo >> 32) * 0x85EBCA6Bu) ^ ((uint32_t)hi * 0xC2B2AE35u) ^
+                 ((uint32_t)(hi >> 32) * 0x27D4EB2Fu);
+    t ^= t >> 15;
+    t *= 0x2C1B3C6Du;
+    line1 = (t >> 20) & (uint32_t)(kColorLines - 1);
+    line2 = line1 ^ (((t >> 9) & (uint32_t)(kColorLines - 1)) | 1u);
+}
+
+// does the tile list a picture substance?  (warp-cooperative)
+__device__ __forceinline__ bool tileHasPictures(const FrameParams& P, const gudni_tile& tile) {
+    const int lane = threadIdx.x & 31;
+    bool any = false;
+    for (uint32_t i = lane; i < tile.shape_count; i += 32)
+        any = any || (tagMeta(__ldg(&P.shapes[tile.shape_start + i].tag)) & kMetaPicture);
+    return __any_sync(0xffffffffu, any);
+}
+
+// Warp-uniform state of the resolve kernel's stack numbering.
+struct RefSlab {
+    unsigned int base;    // first number of the warp's current slab; kRefNone: none drawn yet
+    unsigned int used;
+    int tileIndex;        // the tile the slab's stacks belong to
+};
+__device__ __forceinline__ void closeSlab(const FrameParams& P, RefSlab& slab) {
+    if ((threadIdx.x & 31) == 0 && slab.base != kRefNone)
+        P.refSlabs[slab.base / kRefSlab] = make_uint2((unsigned int)slab.tileIndex, slab.used);
+    slab.base = kRefNone;
+    slab.used = 0;
+}
+
+// One warp, one (tile, 32-column group) of a dense tile without pictures.  Returns per lane 1 if the stack table
+// ran out under this thread (it is handed to the replay).
+__device__ __forceinline__ int resolveWarp(const FrameParams& P, ResolveScratch& W, RefSlab& slab, int tileIndex, unsigned unit) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    if (slab.tileIndex != tileIndex) {   // numbers are only shared inside a tile: new slab, empty cache
+        closeSlab(P, slab);
+        slab.tileIndex = tileIndex;
+        for (int i = lane; i < kColorLines; i += 32) W.ref[i] = kRefNone;
+    }
+    ThreadRec* recp = P.threadRecs + (size_t)unit * 32 + lane;
+    const ThreadRec rec = *recp;
+    ShapeStack base{rec.lo, rec.hi}, cur{rec.lo, rec.hi};
+    uint2* chunk = P.streamPool + (size_t)rec.chunk * kChunkRecs;
+    int pos = 0;
+    bool done = rec.count == kRecInactive;
+    bool failed = false;
+    __syncwarp();
+    for (;;) {
+        if (!__any_sync(full, !done)) break;
+        uint2 r = make_uint2(kRecFlip | kRecNoBit, 0u);
+        if (!done) r = chunk[pos];
+        const uint32_t kind = r.x & kRecKindMask;
+        const uint32_t bit = r.x & kRecBitMask;
+        bool need = false;
+        if (!done) {
+            if (kind == kRecSection) {
+                if (r.x & kRecFirst) cur = base;   // K.cl:1756-1759: the band that ended is un-toggled
+                need = __uint_as_float(r.y) != 0.0f;
+            } else if (kind == kRecFlip) {
+                if (bit != kRecNoBit) base.flip(bit);
+            } else if (kind == kRecLink) {
+                if (r.y == kStreamEnd) done = true;
+                else { chunk = P.streamPool + (size_t)r.y * kChunkRecs; pos = -1; }
+            }
+        }
+        // ---- the stack's number: from the cache, or a new one ------------------------------------------
+        uint32_t ref = kRefNone, line = 0;
+        bool claimed = false;
+        if (need) {
+            uint32_t line2;
+            colorLines(cur.hi, cur.lo, line, line2);
+            const uint32_t r1 = W.ref[line], r2 = W.ref[line2];
+            const ulonglong2 k1 = W.key[line];
+            if (r1 != kRefNone && k1.x == cur.lo && k1.y == cur.hi) {
+                ref = r1;
+            } else {
+                const ulonglong2 k2 = W.key[line2];
+                if (r2 != kRefNone && k2.x == cur.lo && k2.y == cur.hi) {
+                    ref = r2;
+                } else {   // a new stack: an empty line if there is one, else the first line's stack is evicted
+                    if (r1 != kRefNone && r2 == kRefNone) line = line2;
+                    claimed = true;
+                    W.claim[line] = (uint8_t)lane;
+                }
+            }
+        }
+        if (__any_sync(full, claimed)) {
+            __syncwarp();
+            const bool winner = claimed && W.claim[line] == (uint8_t)lane;   // one per line; a loser looks again next round
+            const unsigned winners = __ballot_sync(full, winner);
+            const unsigned int n = (unsigned int)__popc(winners);
+            if (slab.base == kRefNone || slab.used + n > kRefSlab) {
+                closeSlab(P, slab);
+                unsigned int s = 0;
+                if (lane == 0) s = (unsigned int)atomicAdd(&P.counters[kCntRefSlabs], 1ull);
+                s = __shfl_sync(full, s, 0);
+                if (s >= P.refCapSlabs) {   // table full: the warp's remaining threads go to the replay
+                    failed = failed || !done;
+                    done = true;
+                    continue;
+                }
+                slab.base = s * kRefSlab;
+            }
+            if (winner) {
+                ref = slab.base + slab.used + (unsigned int)__popc(winners & ((1u << lane) - 1u));
+                P.stackKeys[ref] = make_ulonglong2(cur.lo, cur.hi);
+                W.key[line] = make_ulonglong2(cur.lo, cur.hi);
+                W.ref[line] = ref;
+            }
+            slab.used += n;
+            __syncwarp();
+        }
+        if (!done && (!need || ref != kRefNone)) {
+            if (need) chunk[pos].x = ref;   // kind bits 00: still a SEC record
+            if (kind == kRecSection && bit != kRecNoBit) cur.flip(bit);   // K.cl:1907-1910
+            pos++;
+        }
+    }
+    if (failed) recp->count = kRecInactive;
+    return failed ? 1 : 0;
+}
+
+// determineColor (K.cl:1447-1513) against a table of premultiplied colours and meta words indexed by stack bit
+struct TileTable {
+    float4 premul[kWarpTableCap];        // 2,048 B
+    uint32_t meta[kWarpTableCap];        //   512 B
+};
+// fills the table (warp-cooperative); returns through the flags what kind of substances the tile lists
+__device__ __forceinline__ void buildTileTable(const FrameParams& P, TileTable& T, const gudni_tile& tile, bool& anyPicture, bool& anyWild) {
+    const int lane = threadIdx.x & 31;
+    bool pic = false, wild = false;
+    for (uint32_t i = lane; i < tile.shape_count; i += 32) {
+        const uint32_t meta = tagMeta(__ldg(&P.shapes[tile.shape_start + i].tag));
+        T.meta[i] = meta;
+        pic = pic || (meta & kMetaPicture);
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(meta & kMetaPicture)) {
+            c = __ldg(P.substances + (meta & kMetaIdMask));
+            wild = wild || !substanceIsTame(c);
+            c = premultiply(c);
+        }
+        T.premul[i] = c;
+    }
+    anyPicture = __any_sync(0xffffffffu, pic);
+    anyWild = __any_sync(0xffffffffu, wild);
+}
+
+__device__ __forceinline__ float4 stackColorTame(const TileTable& T, uint64_t hi, uint64_t lo, float4 bgPremul) {
+    float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t lastId = 0xFFFFFFFFu;
+    uint32_t word = (uint32_t)(hi >> 32);
+    int wordBase = 96;
+    for (;;) {
+        while (word == 0u) {
+            if (wordBase == 0) return compositeOverPremulT<false>(base, bgPremul);
+            wordBase -= 32;
+            word = (wordBase == 64) ? (uint32_t)hi : (wordBase == 32) ? (uint32_t)(lo >> 32) : (uint32_t)lo;
+        }
+        const int b = 31 - __clz((int)word);
+        word ^= (1u << b);
+        const int bit = wordBase + b;
+        const uint32_t meta = T.meta[bit];
+        const uint32_t id = meta & kMetaIdMask;
+        if (id != lastId && (meta & kMetaSet)) {
+            base = compositeOverPremulT<false>(base, T.premul[bit]);
+            if (base.w == 1.0f) return base;
+        }
+        lastId = id;
+    }
+}
+__device__ __forceinline__ float4 stackColorAny(const FrameParams& P, const TileTable& T, uint64_t hi, uint64_t lo, float4 bgPremul,
+                                                int absX, int absY) {
+    float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t lastId = 0xFFFFFFFFu;
+    uint32_t word = (uint32_t)(hi >> 32);
+    int wordBase = 96;
+    for (;;) {
+        while (word == 0u) {
+            if (wordBase == 0) return compositeOverPremul(base, bgPremul);
+            wordBase -= 32;
+            word = (wordBase == 64) ? (uint32_t)hi : (wordBase == 32) ? (uint32_t)(lo >> 32) : (uint32_t)lo;
+        }
+        const int b = 31 - __clz((int)word);
+        word ^= (1u << b);
+        const int bit = wordBase + b;
+        const uint32_t meta = T.meta[bit];
+        const uint32_t id = meta & kMetaIdMask;
+        if (id != lastId && (meta & kMetaSet)) {
+            float4 pm = T.premul[bit];
+            if (meta & kMetaPicture) pm = premultiply(readPicture(P, id, absX, absY));
+            base = compositeOverPremul(base, pm);
+            if (base.w == 1.0f) return base;
+        }
+        lastId = id;
+    }
+}
+
+// One warp, one slab of the stack table.
+__device__ __forceinline__ void compositeSlab(const FrameParams& P, TileTable& T, int& tableTile, bool& tame, unsigned int s) {
+    const int lane = threadIdx.x & 31;
+    const uint2 info = P.refSlabs[s];
+    if ((int)info.x != tableTile) {
+        __syncwarp();
+        bool anyPicture, anyWild;
+        buildTileTable(P, T, P.tiles[info.x], anyPicture, anyWild);
+        tame = !anyWild && substanceIsTame(P.background);
+        tableTile = (int)info.x;
+        __syncwarp();
+    }
+    const float4 bgPremul = premultiply(P.background);
+    for (unsigned int i = lane; i < info.y; i += 32) {
+        const unsigned int ref = s * kRefSlab + i;
+        const ulonglong2 key = P.stackKeys[ref];
+        const float4 c = tame ? stackColorTame(T, key.y, key.x, bgPremul) : stackColorAny(P, T, key.y, key.x, bgPremul, 0, 0);
+        P.stackColors[ref] = c;
+    }
+}
+
+// writePixelGlobal (K.cl:1853-1862) for a finished pixel and the n - 1 untouched rows below it that equal it
+__device__ __forceinline__ void storePixels(const FrameParams& P, uint32_t* outp, int& wrow, int rep, float accR, float accG,
+                                            float accB, float accArea) {
+    const uint32_t word = pixelWord(accR, accG, accB, accArea);
+    for (int k = 0; k < rep; k++) outp[(size_t)(wrow + k) * P.width] = word;
+    wrow += rep;
+}
+
+// One warp, one (tile, 32-column group) of a dense tile without pictures: the resolved streams again, now with
+// the colours at hand.
+__device__ __forceinline__ void accumulateWarp(const FrameParams& P, const gudni_tile& tile, unsigned unit, int column) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const ThreadGeom g = threadGeom(P, tile, column);
+    const ThreadRec rec = P.threadRecs[(size_t)unit * 32 + lane];
+    uint32_t* outp = P.out + (size_t)(g.originY - P.rowOrigin) * P.width + g.originX;   // only dereferenced when active
+    const uint2* chunk = P.streamPool + (size_t)rec.chunk * kChunkRecs;
+    int pos = 0;
+    bool done = rec.count == kRecInactive;
+    float accR = 0.f, accG = 0.f, accB = 0.f, accArea = 0.f;
+    int wrow = 0;
+    for (;;) {
+        if (!__any_sync(full, !done)) break;
+        if (done) continue;
+        const uint2 r = chunk[pos++];
+        const uint32_t kind = r.x & kRecKindMask;
+        if (kind == kRecSection) {
+            const float area = __uint_as_float(r.y);
+            if (area != 0.0f) {
+                const float4 c = P.stackColors[r.x & kRefMask];
+                accR += c.x * area;   // K.cl:1904
+                accG += c.y * area;
+                accB += c.z * area;
+                accArea += area;
+            }
+        } else if (kind == kRecPixelEnd) {
+            storePixels(P, outp, wrow, (int)(r.x & 0xFFFFu), accR, accG, accB, accArea);
+            accR = accG = accB = accArea = 0.f;
+        } else if (kind == kRecLink) {
+            if (r.y == kStreamEnd) done = true;
+            else { chunk = P.streamPool + (size_t)r.y * kChunkRecs; pos = 0; }
+        }
+    }
+}
+
+// One warp, one (tile, 32-column group) of a dense tile WITH pictures: one pass over the unresolved streams,
+// every lane composites the sections of its own pixels.
+__device__ __forceinline__ void pictureWarp(const FrameParams& P, const TileTable& T, const gudni_tile& tile, unsigned unit, int column) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const ThreadGeom g = threadGeom(P, tile, column);
+    const ThreadRec rec = P.threadRecs[(size_t)unit * 32 + lane];
+    const float4 bgPremul = premultiply(P.background);
+    uint32_t* outp = P.out + (size_t)(g.originY - P.rowOrigin) * P.width + g.originX;
+    ShapeStack base{rec.lo, rec.hi}, cur{rec.lo, rec.hi};
+    const uint2* chunk = P.streamPool + (size_t)rec.chunk * kChunkRecs;
+    int pos = 0;
+    bool done = rec.count == kRecInactive;
+    float accR = 0.f, accG = 0.f, accB = 0.f, accArea = 0.f;
+    int wrow = 0;
+    for (;;) {
+        if (!__any_sync(full, !done)) break;
+        // everything up to the next section with an area
+        float area = 0.0f;
+        uint32_t bit = kRecNoBit;
+        while (!done && area == 0.0f) {
+            const uint2 r = chunk[pos++];
+            const uint32_t kind = r.x & kRecKindMask;
+            if (kind == kRecSection) {
+                if (r.x & kRecFirst) cur = base;
+                area = __uint_as_float(r.y);
+                bit = r.x & kRecBitMask;
+                if (area == 0.0f && bit != kRecNoBit) cur.flip(bit);
+            } else if (kind == kRecFlip) {
+                base.flip(r.x & kRecBitMask);
+            } else if (kind == kRecPixelEnd) {
+                storePixels(P, outp, wrow, (int)(r.x & 0xFFFFu), accR, accG, accB, accArea);
+                accR = accG = accB = accArea = 0.f;
+            } else if (r.y == kStreamEnd) {
+                done = true;
+            } else {
+                chunk = P.streamPool + (size_t)r.y * kChunkRecs;
+                pos = 0;
+            }
+        }
+        __syncwarp();
+        if (!done) {
+            const float4 c = stackColorAny(P, T, cur.hi, cur.lo, bgPremul, g.originX, g.originY + wrow);
+            accR += c.x * area;
+            accG += c.y * area;
+            accB += c.z * area;
+            accArea += area;
+            if (bit != kRecNoBit) cur.flip(bit);
+        }
+    }
+}
+
+}  // namespace gudni_dev

@@ -242,7 +242,7 @@ struct GenScratch {
 typedef WarpQueue<kQueueCap, kGenQueueHot> GenQueue;
 
 __device__ __forceinline__ int generateWarp(const FrameParams& P, GenQueue& q, const gudni_tile& tile, int tileIndex,
-                                            unsigned unit, int column, int& generated) {
+                                            unsigned unit, int column, int& generated, bool& exhausted) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const ThreadGeom g = threadGeom(P, tile, column);
@@ -276,7 +276,9 @@ __device__ __forceinline__ int generateWarp(const FrameParams& P, GenQueue& q, c
     unsigned long long base = 0;
     if (lane == 0 && total) base = atomicAdd(&P.counters[kCntStoreCursor], (unsigned long long)total);
     base = __shfl_sync(full, base, 0);
+    exhausted = false;
     if (base + (unsigned long long)total > P.storeCap) {   // store exhausted: the replay kernel takes the warp's threads
+        exhausted = g.active && !spilled;
         spilled = spilled || g.active;
         count = 0;
     }
@@ -290,7 +292,7 @@ __device__ __forceinline__ int generateWarp(const FrameParams& P, GenQueue& q, c
     rec.hi = stack.hi; rec.lo = stack.lo;
     rec.offset = offset;
     rec.count = (g.active && !spilled) ? (unsigned int)count : kRecInactive;
-    rec.pad0 = rec.pad1 = 0u;
+    rec.chunk = 0u; rec.pad1 = 0u;
     P.threadRecs[(size_t)unit * 32 + lane] = rec;
     return spilled ? 1 : 0;
 }

@@ -55,6 +55,12 @@ FrameParams makeParams(gudni_ctx* ctx) {
     P.threadRecs = ctx->threadRecs.as<gudni_dev::ThreadRec>();
     P.strandBounds = ctx->strandBounds.as<float2>();
     P.tileOrder = ctx->tileOrder.as<uint32_t>();
+    P.streamPool = ctx->streamPool.as<uint2>();
+    P.streamCapChunks = (unsigned int)std::min<unsigned long long>(ctx->streamCapChunks, 0xFFFFFFF0ull);
+    P.stackKeys = ctx->stackKeys.as<ulonglong2>();
+    P.stackColors = ctx->stackColors.as<float4>();
+    P.refSlabs = ctx->refSlabs.as<uint2>();
+    P.refCapSlabs = (unsigned int)std::min<unsigned long long>(ctx->refCapSlabs, (0x3FFFFFFFull / 128));
     return P;
 }
 
@@ -64,18 +70,33 @@ int ensureFrameBuffer(gudni_ctx* ctx) {
     return devEnsure(ctx, ctx->frame, std::max<size_t>(bytes, 4));
 }
 
-// Hand-over buffers between the generate and the sweep kernel: room for 16 thresholds per
-// column-thread or one per four pixels, whichever is more, and at least 25 % above what the previous
-// frame asked for (warps that find the store full hand their threads to the replay kernel, so an
-// undersized first frame is slow, not wrong); one 32-byte record per thread.
+// Hand-over buffers between the kernels.  Threshold store (generate -> slice): a first guess of 12 thresholds
+// + the 8 slack entries (kStoreSlack) per column-thread or one per four pixels, whichever is more.  Section
+// stream pool (slice -> colour): 6 chunks of 16 records per column-thread + one per 64 pixels.  Both first
+// guesses are capped by a byte budget; afterwards each is sized 25 % above what the previous frame drew.  A frame
+// that runs one of them dry hands the threads that found it empty to the replay kernel and frame_end then
+// rasterizes the frame again with the measured demand (see retryExhausted), so an undersized guess costs time on
+// the first frame, never pixels.  One 32-byte record per thread.
+constexpr size_t kFirstGuessBudget = (size_t)6 << 30;
 int ensureHandover(gudni_ctx* ctx, int64_t totalTiles) {
     const size_t threads = (size_t)totalTiles * (size_t)ctx->spec.threads_per_tile;
     const size_t pixels = (size_t)ctx->width * (size_t)(ctx->rowEnd - ctx->rowBegin);
-    // first guess: 16 thresholds + the 8 slack entries (kStoreSlack) per column-thread; afterwards the last frame's demand
-    const size_t entries = std::max({threads * 24, pixels / 4, (size_t)(ctx->storeDemand + ctx->storeDemand / 4), (size_t)1 << 20});
+    const size_t guess = std::min(std::max(threads * 20, pixels / 4), kFirstGuessBudget / 20);
+    const size_t entries = std::max({guess, (size_t)(ctx->storeDemand + ctx->storeDemand / 4), (size_t)1 << 20});
     GUDNI_TRY(devEnsure(ctx, ctx->thrStore, entries * 16));
     GUDNI_TRY(devEnsure(ctx, ctx->hdrStore, entries * 4));
     ctx->storeCap = std::min(ctx->thrStore.cap / 16, ctx->hdrStore.cap / 4);
+    const size_t chunkGuess = std::min(threads * 6 + pixels / 64, kFirstGuessBudget / 128);
+    const size_t chunks = std::max({chunkGuess, (size_t)(ctx->streamDemand + ctx->streamDemand / 4), (size_t)1 << 14});
+    GUDNI_TRY(devEnsure(ctx, ctx->streamPool, chunks * 128));
+    ctx->streamCapChunks = ctx->streamPool.cap / 128;
+    // stack table: slabs of 128 numbers; first guess two slabs per (tile, 32-column group) + one number per 2 pixels
+    const size_t slabGuess = std::min(threads / 16 + pixels / 256, kFirstGuessBudget / (128 * 32));
+    const size_t slabs = std::max({slabGuess, (size_t)(ctx->refDemand + ctx->refDemand / 4), (size_t)1 << 10});
+    GUDNI_TRY(devEnsure(ctx, ctx->stackKeys, slabs * 128 * 16));
+    GUDNI_TRY(devEnsure(ctx, ctx->stackColors, slabs * 128 * 16));
+    GUDNI_TRY(devEnsure(ctx, ctx->refSlabs, slabs * 8));
+    ctx->refCapSlabs = std::min({ctx->stackKeys.cap / (128 * 16), ctx->stackColors.cap / (128 * 16), ctx->refSlabs.cap / 8});
     GUDNI_TRY(devEnsure(ctx, ctx->threadRecs, std::max<size_t>(threads, 32) * sizeof(gudni_dev::ThreadRec)));
     GUDNI_TRY(devEnsure(ctx, ctx->tileOrder, (size_t)std::max<int64_t>(totalTiles, 1) * 4, (size_t)ctx->rasteredTiles * 4));
     return GUDNI_OK;
@@ -181,7 +202,7 @@ void gudni_b200_destroy(gudni_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->geometry, &ctx->substances, &ctx->pictures, &ctx->pictureUses, &ctx->shapes, &ctx->tiles,
                       &ctx->tileThreadBase, &ctx->frame, &ctx->counters, &ctx->spillList, &ctx->spillThr, &ctx->spillHdr,
                       &ctx->dbgThresholds, &ctx->dbgShapeBits, &ctx->entries, &ctx->binCounters, &ctx->thrStore, &ctx->hdrStore,
-                      &ctx->threadRecs, &ctx->strandBounds, &ctx->tileOrder, &ctx->olShapes, &ctx->olOutlines, &ctx->olPairs,
+                      &ctx->threadRecs, &ctx->streamPool, &ctx->stackKeys, &ctx->stackColors, &ctx->refSlabs, &ctx->strandBounds, &ctx->tileOrder, &ctx->olShapes, &ctx->olOutlines, &ctx->olPairs,
                       &ctx->olTransforms, &ctx->strandMeasures, &ctx->strandScan, &ctx->strandTotals};
     for (DevBuf* b : bufs)
         if (b->ptr) cudaFree(b->ptr);
@@ -455,22 +476,43 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     } else {
         markFirstKernel(ctx);
     }
-    GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evRasterDone, ctx->stream));
     const size_t rows = (size_t)(ctx->rowEnd - ctx->rowBegin);
-    if (out_bgra) {
-        const uint32_t* src = ctx->externalTarget
-                                  ? static_cast<const uint32_t*>(ctx->externalTarget) +
-                                        (size_t)(ctx->rowBegin - ctx->externalRowOrigin) * ctx->width
-                                  : ctx->frame.as<uint32_t>();
-        GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(out_bgra, src, rows * ctx->width * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evDownloadDone, ctx->stream));
     unsigned long long counters[32] = {0};
-    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(counters, ctx->counters.ptr, 256, cudaMemcpyDeviceToHost, ctx->stream));
     unsigned long long binCounters[8] = {0};
-    if (ctx->binUsed)
-        GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(binCounters, ctx->binCounters.ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int attempt = 0;; attempt++) {
+        GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evRasterDone, ctx->stream));
+        if (out_bgra) {
+            const uint32_t* src = ctx->externalTarget
+                                      ? static_cast<const uint32_t*>(ctx->externalTarget) +
+                                            (size_t)(ctx->rowBegin - ctx->externalRowOrigin) * ctx->width
+                                      : ctx->frame.as<uint32_t>();
+            GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(out_bgra, src, rows * ctx->width * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evDownloadDone, ctx->stream));
+        GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(counters, ctx->counters.ptr, 256, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->binUsed)
+            GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(binCounters, ctx->binCounters.ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->storeDemand = counters[gudni_dev::kCntStoreCursor];
+        ctx->streamDemand = counters[gudni_dev::kCntStreamCursor];
+        ctx->refDemand = counters[gudni_dev::kCntRefSlabs];
+        // A per-frame buffer ran dry (threshold store, stream pool) or more threads were handed to the replay than
+        // its list holds (those were dropped): the demand is known now, so size the buffers from it and rasterize
+        // the frame's tiles again — everything the kernels read is still resident.  Once: a second failure is reported.
+        const bool dropped = counters[gudni_dev::kCntSpilled] > (unsigned long long)ctx->spillCapacity;
+        if (attempt > 0 || !ctx->nTiles || counters[gudni_dev::kCntNonFinite] || !(dropped || counters[gudni_dev::kCntExhausted])) break;
+        if (dropped) {
+            size_t cap = (size_t)ctx->spillCapacity;
+            while (cap < counters[gudni_dev::kCntSpilled] + counters[gudni_dev::kCntSpilled] / 4) cap *= 2;
+            GUDNI_TRY(devEnsure(ctx, ctx->spillList, cap * 8));
+            ctx->spillCapacity = (int)std::min<size_t>(cap, (size_t)1 << 30);
+        }
+        GUDNI_TRY(ensureHandover(ctx, ctx->nTiles));
+        GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, 256, ctx->stream));
+        GUDNI_TRY(gudni_launch::rasterTiles(ctx, makeParams(ctx), 0, (int)ctx->nTiles));
+        GUDNI_TRY(gudni_launch::rasterSpill(ctx, makeParams(ctx)));
+        ctx->retriedFrames++;
+    }
     ctx->inFrame = false;
 #ifdef GUDNI_STATS
     fprintf(stderr, "[stats] records %llu ready-hits %llu pending-hits %llu new %llu slow %llu rounds %llu flushes %llu logged %llu\n",
@@ -485,9 +527,12 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     s.n_shape_refs = ctx->nShapes;
     s.n_thresholds = (int64_t)counters[gudni_dev::kCntThresholds];
     s.n_spilled_threads = (int64_t)counters[gudni_dev::kCntSpilled];
-    ctx->storeDemand = counters[gudni_dev::kCntStoreCursor];
-    int64_t dropped = std::max<int64_t>(0, s.n_spilled_threads - ctx->spillCapacity);
-    s.n_overflow_threads = (int64_t)counters[gudni_dev::kCntOverflow] + dropped;
+    // threads the replay list could not hold even after the retry: their pixels were not written
+    const int64_t droppedThreads = std::max<int64_t>(0, s.n_spilled_threads - ctx->spillCapacity);
+    s.n_overflow_threads = (int64_t)counters[gudni_dev::kCntOverflow];
+    if (droppedThreads > 0)
+        return ctxFail(ctx, GUDNI_ERR_OOM, "%lld column-threads could not be replayed (replay list full after one retry): their pixels are missing",
+                       (long long)droppedThreads);
     s.algorithmic_bytes = (int64_t)ctx->geometryBytes + 16 * ctx->nShapes + 32 * ctx->nTiles + 16 * (int64_t)ctx->nSubstances +
                           24 * (int64_t)ctx->nPictureUses + (int64_t)ctx->pictureBytes + 4 * (int64_t)ctx->width * (int64_t)rows;
     cudaEventElapsedTime(&s.ms_upload, ctx->evFrameBegin, ctx->evUploadDone);

@@ -57,6 +57,8 @@ inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyK
 // ---- vector types ---------------------------------------------------------------------------------------
 struct float2 { float x, y; };
 struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 struct uint3 { unsigned x, y, z; };
 struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
 struct uchar4 { unsigned char x, y, z, w; };

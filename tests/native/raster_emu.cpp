@@ -91,6 +91,8 @@ void runBlock(void (*entry)(void*), void* args, dim3 grid, dim3 block, uint3 bid
 using namespace gudni_dev;
 
 static size_t g_storeEntriesOverride;
+static size_t g_streamChunksOverride;
+static size_t g_refSlabsOverride;
 static int g_rowBegin = 0, g_rowEnd = 0;    // raster_emu_set_strip: rows of the canvas this "context" renders (0,0 = all)
 namespace {
 
@@ -149,6 +151,20 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
     P.strandBounds = bounds.data();
     P.tileOrder = order.data();
     P.numStreams = std::max(1, std::min(3, nTiles));
+    // section-stream pool (raster_split.cuh): generous (the shim sizes it from the last frame's demand and retries a frame that ran dry), or what raster_emu_set_stream_chunks forces
+    const size_t chunks = g_streamChunksOverride ? g_streamChunksOverride
+                                                 : std::max<size_t>(threads * 96 + (size_t)in.width * in.height / 16, (size_t)1 << 14);
+    std::vector<uint2> streamPool(chunks * kChunkRecs);
+    P.streamPool = streamPool.data();
+    P.streamCapChunks = (unsigned int)chunks;
+    const size_t refSlabs = g_refSlabsOverride ? g_refSlabsOverride : std::max<size_t>(threads / 4 + (size_t)in.width * in.height / 64, 64);
+    std::vector<ulonglong2> stackKeys(refSlabs * kRefSlab);
+    std::vector<float4> stackColors(refSlabs * kRefSlab);
+    std::vector<uint2> refSlabInfo(refSlabs);
+    P.stackKeys = stackKeys.data();
+    P.stackColors = stackColors.data();
+    P.refSlabs = refSlabInfo.data();
+    P.refCapSlabs = (unsigned int)refSlabs;
     if (dbgThresholds) for (int64_t i = 0; i < nColumns; i++) dbgThresholds[i] = -1;
     if (dbgShapeBits) for (int64_t i = 0; i < nColumns; i++) dbgShapeBits[i] = -1;
     if (nTiles > 0) {
@@ -157,7 +173,15 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
                           static_cast<const uint8_t*>(boundsRecords), boundsStride, (int)nBoundsRecords, bounds.data(), counters.data());
         cuemu::launch(tile_order_kernel, dim3(1), dim3(256), tilesCopy.data(), 0, nTiles, order.data(), counters.data());
         cuemu::launch(raster_generate_kernel, dim3(2), dim3(kGenWarpsPerCta * 32), P, 0, nTiles);
+#if GUDNI_SPLIT_SWEEP
+        cuemu::launch(raster_slice_kernel, dim3(2), dim3(kSliceWarpsPerCta * 32), P, 0, nTiles);
+        cuemu::launch(raster_resolve_kernel, dim3(2), dim3(kResolveWarpsPerCta * 32), P, 0, nTiles);
+        cuemu::launch(raster_composite_kernel, dim3(2), dim3(kCompositeWarpsPerCta * 32), P);
+        cuemu::launch(raster_accumulate_kernel, dim3(2), dim3(kAccumulateWarpsPerCta * 32), P, 0, nTiles);
+        cuemu::launch(raster_picture_kernel, dim3(2), dim3(kColorWarpsPerCta * 32), P, 0, nTiles);
+#else
         cuemu::launch(raster_sweep_kernel, dim3(2), dim3(kSweepWarpsPerCta * 32), P, 0, nTiles);
+#endif
         cuemu::launch(raster_spill_kernel, dim3(1), dim3(spillSlots), P, spillThr.data(), spillHdr.data(), spillSlots);
     }
     (void)nShapes;
@@ -167,6 +191,9 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
         stats[2] = (int64_t)counters[kCntOverflow];
         stats[3] = (int64_t)cuemu::S.switches;
         stats[4] = (int64_t)counters[kCntNonFinite];
+        stats[5] = (int64_t)counters[kCntExhausted];
+        stats[6] = (int64_t)counters[kCntStreamCursor];
+        stats[7] = (int64_t)counters[kCntRefSlabs];
     }
 }
 
@@ -243,6 +270,10 @@ extern "C" {
 // 0 restores the shim's sizing rule.  A store that is too small makes the generate kernel hand whole warps to
 // the replay kernel (raster_warp.cuh generateWarp): slow, not wrong.
 void raster_emu_set_store_entries(size_t n) { g_storeEntriesOverride = n; }
+// the same for the section-stream pool between the slice and the colour kernel (chunks of 16 records)
+void raster_emu_set_stream_chunks(size_t n) { g_streamChunksOverride = n; }
+// ... and for the table of distinct shape stacks (slabs of 128 numbers)
+void raster_emu_set_ref_slabs(size_t n) { g_refSlabsOverride = n; }
 
 // order in which the emulator runs the threads of a CTA between rendezvous points (see runBlock)
 void raster_emu_set_schedule(int mode) { cuemu::scheduleMode = mode; }
