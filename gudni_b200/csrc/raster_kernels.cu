@@ -8,9 +8,6 @@
 
 using namespace gudni_dev;
 
-#ifndef GUDNI_GEN_WARPS
-#define GUDNI_GEN_WARPS 4
-#endif
 #ifndef GUDNI_SWEEP_WARPS
 #define GUDNI_SWEEP_WARPS 2
 #endif
@@ -23,7 +20,6 @@ using namespace gudni_dev;
 #ifndef GUDNI_SPLIT_SWEEP
 #define GUDNI_SPLIT_SWEEP 1     // 1: raster_slice_kernel + raster_color_kernel; 0: round 1's raster_sweep_kernel
 #endif
-constexpr int kGenWarpsPerCta = GUDNI_GEN_WARPS;
 constexpr int kSweepWarpsPerCta = GUDNI_SWEEP_WARPS;
 constexpr int kSliceWarpsPerCta = GUDNI_SLICE_WARPS;
 constexpr int kColorWarpsPerCta = GUDNI_COLOR_WARPS;
@@ -45,11 +41,16 @@ __device__ __forceinline__ void registerSpill(const FrameParams& P, int tileInde
         P.spillList[slot] = ((unsigned long long)tileIndex << 32) | (unsigned long long)column;
 }
 
-#ifndef GUDNI_GEN_MIN_CTAS
-#define GUDNI_GEN_MIN_CTAS 1
+// generateThresholds + sortThresholds (K.cl:2030-2115), one CTA per tile: blockDim.x = threadsPerTile, thread =
+// column-thread.  Dynamic shared memory: the tile's staged strand headers, then one queue window per warp.
+__global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams P, int tileBase, int nTiles) {
+#ifdef GUDNI_HOST_EMULATION
+    unsigned char* smemRaw = cuemu::dynamicShared;
+#else
+    extern __shared__ __align__(16) unsigned char smemRaw[];
 #endif
-__global__ void __launch_bounds__(kGenWarpsPerCta * 32, GUDNI_GEN_MIN_CTAS) raster_generate_kernel(const FrameParams P, int tileBase, int nTiles) {
-    __shared__ GenScratch scratch[kGenWarpsPerCta];
+    TileStage& S = *reinterpret_cast<TileStage*>(smemRaw);
+    GenScratch* scratch = reinterpret_cast<GenScratch*>(smemRaw + ((sizeof(TileStage) + 15) & ~(size_t)15));
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     QueueCold<kQueueCap - kGenQueueHot> cold;
@@ -60,25 +61,34 @@ __global__ void __launch_bounds__(kGenWarpsPerCta * 32, GUDNI_GEN_MIN_CTAS) rast
     q.hdrHot = scratch[warp].qHdr + lane;
     const int warpShift = P.computeDepth - 5;                    // warps per tile = threadsPerTile / 32
     const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
-    unsigned int* cursors = reinterpret_cast<unsigned int*>(P.counters + 32);
-    StreamCursor cursor;
-    cursor.init(P.numStreams);
+    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkGenerate);
     for (;;) {
-        unsigned int tileSlot, warpInTile;
-        if (!streamNext(cursor, cursors, P.numStreams, nTiles, warpShift, tileSlot, warpInTile)) break;
-        const int tileIndex = (int)P.tileOrder[tileBase + (int)tileSlot];
-        const int column = (int)(warpInTile << 5) + lane;
-        const unsigned recUnit = ((unsigned)tileIndex << warpShift) + warpInTile;   // thread records are indexed by tile, not by hand-out order
+        __syncthreads();
+        if (threadIdx.x == 0) S.tileSlot = (int)atomicAdd(workCounter, 1u);
+        __syncthreads();
+        const int tileSlot = S.tileSlot;
+        if (tileSlot >= nTiles) break;
+        const int tileIndex = (int)P.tileOrder[tileBase + tileSlot];
+        const int column = (int)threadIdx.x;
+        const unsigned recUnit = ((unsigned)tileIndex << warpShift) + (unsigned)warp;   // thread records are indexed by tile, not by hand-out order
         const gudni_tile tile = P.tiles[tileIndex];
+        const ThreadGeom g = threadGeom(P, tile, column);
         int generated = -1;
         int failed = 0;
         bool exhausted = false;
         if (tile.shape_count <= denseCap) {
-            failed = generateWarp(P, q, tile, tileIndex, recUnit, column, generated, exhausted);
+            GenThread t;
+            t.stack = ShapeStack{0ull, 0ull};
+            t.bits = 0u;
+            t.f = GenFlags{false, false};
+            t.enclosedByShape = false;
+            t.failed = false;
+            q.init();
+            generateTileThresholds(P, S, q, t, tile, g);
+            failed = packWarp(P, q, g, t.stack, t.bits, t.failed, tileIndex, recUnit, column, generated, exhausted);
         } else {
             // a tile that stopped splitting at the 8-pixel floor with more shapes than stack bits:
             // its threads take the lane-private replay path (bit -> shape table, HBM queue)
-            const ThreadGeom g = threadGeom(P, tile, column);
             ThreadRec rec{};
             rec.count = kRecInactive;
             P.threadRecs[(size_t)recUnit * 32 + lane] = rec;
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(kSweepWarpsPerCta * 32, GUDNI_SWEEP_MIN_CTAS) 
 
 // The sweep's state machine alone (raster_split.cuh): sorted thresholds in, section streams out.
 #ifndef GUDNI_SLICE_MIN_CTAS
-#define GUDNI_SLICE_MIN_CTAS 1
+#define GUDNI_SLICE_MIN_CTAS 8      // 64 registers: 32 warps per SM hide the divergent kernel's latencies (96 registers / 20 warps: +1.1 ms on S4)
 #endif
 __global__ void __launch_bounds__(kSliceWarpsPerCta * 32, GUDNI_SLICE_MIN_CTAS) raster_slice_kernel(const FrameParams P, int tileBase, int nTiles) {
     __shared__ SliceScratch scratch[kSliceWarpsPerCta];
@@ -404,12 +414,16 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     FrameParams P = frame;
     // occupancy of the persistent kernels on THIS context's device (a process may hold several contexts)
     const size_t sweepSmem = kSweepWarpsPerCta * sizeof(WarpScratch);
+    const size_t genSmem = ((sizeof(TileStage) + 15) & ~(size_t)15) + (size_t)(ctx->spec.threads_per_tile / 32) * sizeof(GenScratch);
     if (!ctx->occupancyKnown) {
         GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweepSmem));
         GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sweepCtasPerSm, raster_sweep_kernel,
                                                                           kSweepWarpsPerCta * 32, sweepSmem));
+        // the attribute belongs to the function, not to the context: allow what the largest spec (1,024 threads per tile) needs
+        const size_t genSmemMax = ((sizeof(TileStage) + 15) & ~(size_t)15) + (size_t)32 * sizeof(GenScratch);
+        GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmemMax));
         GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->genCtasPerSm, raster_generate_kernel,
-                                                                          kGenWarpsPerCta * 32, 0));
+                                                                          ctx->spec.threads_per_tile, genSmem));
         GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_slice_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sliceCtasPerSm, raster_slice_kernel,
                                                                           kSliceWarpsPerCta * 32, 0));
@@ -436,6 +450,7 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     // work counters of the kernels (the threshold store and stream cursors run on across the jobs of a frame)
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 32, 0, gudni_dev::kMaxSms * sizeof(unsigned int), ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkSweep, 0, 8, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkGenerate, 0, 8, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkColor, 0, 8, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkResolve, 0, 24, ctx->stream));
     const long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
@@ -444,7 +459,7 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     };
     tile_order_kernel<<<1, 1024, 0, ctx->stream>>>(const_cast<gudni_tile*>(P.tiles), tileBase, nTiles, const_cast<uint32_t*>(P.tileOrder), P.counters);
     ctx->launches++;
-    raster_generate_kernel<<<grid(ctx->genCtasPerSm, kGenWarpsPerCta), kGenWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
+    raster_generate_kernel<<<std::min(ctx->genCtasPerSm * numSms, nTiles), ctx->spec.threads_per_tile, genSmem, ctx->stream>>>(P, tileBase, nTiles);
     ctx->launches++;
 #if GUDNI_SPLIT_SWEEP
     raster_slice_kernel<<<grid(ctx->sliceCtasPerSm, kSliceWarpsPerCta), kSliceWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);

@@ -247,6 +247,24 @@ __device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, 
     return spilled ? 1 : 0;
 }
 
+// Reads a stream two records (16 bytes) at a time: chunks are 128-byte aligned, records 8 bytes.
+struct StreamReader {
+    const uint2* chunk;
+    int pos;
+    uint4 pair;   // records (pos & ~1) and (pos | 1)
+    __device__ __forceinline__ void open(const uint2* pool, unsigned int first) {
+        chunk = pool + (size_t)first * kChunkRecs;
+        pos = 0;
+        pair = *reinterpret_cast<const uint4*>(chunk);
+    }
+    __device__ __forceinline__ uint2 get() const { return (pos & 1) ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y); }
+    __device__ __forceinline__ void next() {
+        pos++;
+        if (!(pos & 1)) pair = *reinterpret_cast<const uint4*>(chunk + pos);
+    }
+    __device__ __forceinline__ void jump(const uint2* pool, unsigned int c) { open(pool, c); }
+};
+
 // ---- colours: resolve -> composite -> accumulate ------------------------------------------------------------
 // The section streams are replayed twice.  raster_resolve_kernel rebuilds the shape stack of every section from
 // the toggles and gives every *distinct* stack a number (a per-warp cache in shared memory keyed by the 128-bit
@@ -320,15 +338,15 @@ __device__ __forceinline__ int resolveWarp(const FrameParams& P, ResolveScratch&
     ThreadRec* recp = P.threadRecs + (size_t)unit * 32 + lane;
     const ThreadRec rec = *recp;
     ShapeStack base{rec.lo, rec.hi}, cur{rec.lo, rec.hi};
-    uint2* chunk = P.streamPool + (size_t)rec.chunk * kChunkRecs;
-    int pos = 0;
     bool done = rec.count == kRecInactive;
     bool failed = false;
+    StreamReader in;
+    in.chunk = P.streamPool; in.pos = 0; in.pair = make_uint4(0u, 0u, 0u, 0u);
+    if (!done) in.open(P.streamPool, rec.chunk);
     __syncwarp();
     for (;;) {
         if (!__any_sync(full, !done)) break;
-        uint2 r = make_uint2(kRecFlip | kRecNoBit, 0u);
-        if (!done) r = chunk[pos];
+        const uint2 r = done ? make_uint2(kRecFlip | kRecNoBit, 0u) : in.get();
         const uint32_t kind = r.x & kRecKindMask;
         const uint32_t bit = r.x & kRecBitMask;
         bool need = false;
@@ -338,9 +356,6 @@ __device__ __forceinline__ int resolveWarp(const FrameParams& P, ResolveScratch&
                 need = __uint_as_float(r.y) != 0.0f;
             } else if (kind == kRecFlip) {
                 if (bit != kRecNoBit) base.flip(bit);
-            } else if (kind == kRecLink) {
-                if (r.y == kStreamEnd) done = true;
-                else { chunk = P.streamPool + (size_t)r.y * kChunkRecs; pos = -1; }
             }
         }
         // ---- the stack's number: from the cache, or a new one ------------------------------------------
@@ -366,7 +381,7 @@ __device__ __forceinline__ int resolveWarp(const FrameParams& P, ResolveScratch&
         }
         if (__any_sync(full, claimed)) {
             __syncwarp();
-            const bool winner = claimed && W.claim[line] == (uint8_t)lane;   // one per line; a loser looks again next round
+            const bool winner = claimed && W.claim[line] == (uint8_t)lane;   // one per line
             const unsigned winners = __ballot_sync(full, winner);
             const unsigned int n = (unsigned int)__popc(winners);
             if (slab.base == kRefNone || slab.used + n > kRefSlab) {
@@ -389,11 +404,20 @@ __device__ __forceinline__ int resolveWarp(const FrameParams& P, ResolveScratch&
             }
             slab.used += n;
             __syncwarp();
+            if (claimed && !winner) {   // neighbouring columns tend to meet a new stack in the same round: share the winner's number
+                const ulonglong2 k = W.key[line];
+                if (k.x == cur.lo && k.y == cur.hi) ref = W.ref[line];   // (else: look again next round)
+            }
         }
         if (!done && (!need || ref != kRefNone)) {
-            if (need) chunk[pos].x = ref;   // kind bits 00: still a SEC record
+            if (need) const_cast<uint2*>(in.chunk)[in.pos].x = ref;   // kind bits 00: still a SEC record
             if (kind == kRecSection && bit != kRecNoBit) cur.flip(bit);   // K.cl:1907-1910
-            pos++;
+            if (kind == kRecLink) {
+                if (r.y == kStreamEnd) done = true;
+                else in.jump(P.streamPool, r.y);
+            } else {
+                in.next();
+            }
         }
     }
     if (failed) recp->count = kRecInactive;
@@ -512,32 +536,45 @@ __device__ __forceinline__ void accumulateWarp(const FrameParams& P, const gudni
     const ThreadGeom g = threadGeom(P, tile, column);
     const ThreadRec rec = P.threadRecs[(size_t)unit * 32 + lane];
     uint32_t* outp = P.out + (size_t)(g.originY - P.rowOrigin) * P.width + g.originX;   // only dereferenced when active
-    const uint2* chunk = P.streamPool + (size_t)rec.chunk * kChunkRecs;
-    int pos = 0;
     bool done = rec.count == kRecInactive;
+    StreamReader in;
+    in.chunk = P.streamPool; in.pos = 0; in.pair = make_uint4(0u, 0u, 0u, 0u);
+    if (!done) in.open(P.streamPool, rec.chunk);
     float accR = 0.f, accG = 0.f, accB = 0.f, accArea = 0.f;
     int wrow = 0;
+    // Two alternating phases so that the lanes run the same code: (1) every lane adds up the sections of its
+    // current pixel — a short loop of a few instructions per section; (2) the lanes that finished a pixel
+    // convert and store it together (three divisions and the stores: K.cl:1853-1862).
     for (;;) {
-        if (!__any_sync(full, !done)) break;
-        if (done) continue;
-        const uint2 r = chunk[pos++];
-        const uint32_t kind = r.x & kRecKindMask;
-        if (kind == kRecSection) {
-            const float area = __uint_as_float(r.y);
-            if (area != 0.0f) {
-                const float4 c = P.stackColors[r.x & kRefMask];
-                accR += c.x * area;   // K.cl:1904
-                accG += c.y * area;
-                accB += c.z * area;
-                accArea += area;
+        int rep = 0;
+        while (!done && rep == 0) {
+            const uint2 r = in.get();
+            const uint32_t kind = r.x & kRecKindMask;
+            if (kind == kRecLink) {
+                if (r.y == kStreamEnd) done = true;
+                else in.jump(P.streamPool, r.y);
+                continue;
             }
-        } else if (kind == kRecPixelEnd) {
-            storePixels(P, outp, wrow, (int)(r.x & 0xFFFFu), accR, accG, accB, accArea);
-            accR = accG = accB = accArea = 0.f;
-        } else if (kind == kRecLink) {
-            if (r.y == kStreamEnd) done = true;
-            else { chunk = P.streamPool + (size_t)r.y * kChunkRecs; pos = 0; }
+            in.next();
+            if (kind == kRecSection) {
+                const float area = __uint_as_float(r.y);
+                if (area != 0.0f) {
+                    const float4 c = P.stackColors[r.x & kRefMask];
+                    accR += c.x * area;   // K.cl:1904
+                    accG += c.y * area;
+                    accB += c.z * area;
+                    accArea += area;
+                }
+            } else if (kind == kRecPixelEnd) {
+                rep = (int)(r.x & 0xFFFFu);
+            }
         }
+        __syncwarp();
+        if (rep) {
+            storePixels(P, outp, wrow, rep, accR, accG, accB, accArea);
+            accR = accG = accB = accArea = 0.f;
+        }
+        if (!__any_sync(full, !done)) break;
     }
 }
 

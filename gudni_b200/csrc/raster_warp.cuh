@@ -36,7 +36,7 @@ constexpr int kQueueCap = GUDNI_QUEUE_CAP;          // thresholds per column-thr
 #endif
 constexpr int kQueueHot = GUDNI_QUEUE_HOT;           // head window in shared memory (sweep kernel; power of two)
 #ifndef GUDNI_GEN_QUEUE_HOT
-#define GUDNI_GEN_QUEUE_HOT 8
+#define GUDNI_GEN_QUEUE_HOT 4
 #endif
 constexpr int kGenQueueHot = GUDNI_GEN_QUEUE_HOT;       // ... (generate kernel)
 #ifndef GUDNI_CACHE_LINES
@@ -241,19 +241,16 @@ struct GenScratch {
 };
 typedef WarpQueue<kQueueCap, kGenQueueHot> GenQueue;
 
-__device__ __forceinline__ int generateWarp(const FrameParams& P, GenQueue& q, const gudni_tile& tile, int tileIndex,
-                                            unsigned unit, int column, int& generated, bool& exhausted) {
+__device__ __forceinline__ int packWarp(const FrameParams& P, GenQueue& q, const ThreadGeom& g, const ShapeStack& stack,
+                                        uint32_t bits, bool failed, int tileIndex, unsigned unit, int column, int& generated,
+                                        bool& exhausted) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const ThreadGeom g = threadGeom(P, tile, column);
-    ShapeStack stack{0ull, 0ull};
     bool spilled = false;
     generated = -1;
     int count = 0;
     if (g.active) {
-        q.init();
-        const uint32_t bits = buildThresholds<true>(P, g, q, stack, nullptr);
-        if (q.failed()) {
+        if (failed) {
             spilled = true;
         } else {
             generated = q.len;
@@ -295,6 +292,145 @@ __device__ __forceinline__ int generateWarp(const FrameParams& P, GenQueue& q, c
     rec.chunk = 0u; rec.pad1 = 0u;
     P.threadRecs[(size_t)unit * 32 + lane] = rec;
     return spilled ? 1 : 0;
+}
+
+// ---- generate kernel body, one CTA per tile ---------------------------------------------------------
+// The CTA's threads are the tile's column-threads (blockDim = threadsPerTile), so every thread walks the same
+// shape list.  The reference has each work-item fetch every strand's header from global memory itself
+// (K.cl:1557-1583: size word, right end, left end + control); here the CTA stages the headers of a run of
+// consecutive shapes in shared memory once — one thread per shape walks that shape's strands (the next
+// strand's address hangs on the size word of the one before) and writes them at the offset a scan of the
+// strand counts gives — and then every thread runs down the table: the range tests read shared memory, and only
+// a column the strand really crosses goes on to the strand's tree in global memory.
+struct StrandEntry {   // 48 bytes
+    float4 lc;              // left end, control point of the first curve (K.cl:1371-1373)
+    float2 right;           // right end
+    float2 yb;              // (min y, max y) over the strand's points (strand_bounds_kernel)
+    uint32_t sizeWord;
+    uint32_t offset16;      // the strand's place in the geometry heap, in 16-byte units
+    uint32_t shapeAndFlags; // position of the shape in the tile's list | kEntryFirst | kEntryLast
+    uint32_t pad;
+};
+constexpr uint32_t kEntryFirst = 0x100u, kEntryLast = 0x200u, kEntryShapeMask = 0xFFu;
+#ifndef GUDNI_STRAND_TABLE
+#define GUDNI_STRAND_TABLE 128
+#endif
+constexpr int kStrandTableCap = GUDNI_STRAND_TABLE;
+struct TileStage {
+    StrandEntry entry[kStrandTableCap];
+    uint32_t shapeBase[kWarpTableCap + 1];   // exclusive scan of the strand counts of the tile's shapes
+    int tileSlot;                            // the CTA's current tile
+};
+
+struct GenThread {   // what buildThresholdArray carries from strand to strand and shape to shape (K.cl:1540-1595)
+    ShapeStack stack;
+    uint32_t bits;
+    GenFlags f;
+    bool enclosedByShape;
+    bool failed;
+};
+template <class Q>
+__device__ __forceinline__ void genStrand(const FrameParams& P, Q& q, GenThread& t, float ox, float oy, float floatHeight,
+                                          uint32_t shapeAndFlags, uint32_t sizeWord, const uint8_t* strand, float2 right,
+                                          float4 lc, float2 yb) {
+    const uint32_t n = shapeAndFlags & kEntryShapeMask;
+    if (shapeAndFlags & kEntryFirst) { t.f.added = false; t.enclosedByShape = false; }
+    t.f.enclosed = false;
+    strandThresholds(q, strand, sizeWord, ox, oy, floatHeight, n, t.f, right, lc, P.strandBounds != nullptr, yb);
+    t.enclosedByShape = t.enclosedByShape != t.f.enclosed;
+    if (q.failed()) { t.failed = true; return; }
+    if (shapeAndFlags & kEntryLast) {
+        if (t.enclosedByShape) t.stack.flip(n);
+        if (t.f.added || t.enclosedByShape) t.bits += 1;
+    }
+}
+
+// Whole CTA.  Afterwards q holds the thread's thresholds in push order (or t.failed is set).
+__device__ __forceinline__ void generateTileThresholds(const FrameParams& P, TileStage& S, GenQueue& q, GenThread& t,
+                                                       const gudni_tile& tile, const ThreadGeom& g) {
+    const int tid = threadIdx.x, nThreads = blockDim.x;
+    const float ox = (float)g.originX, oy = (float)g.originY, floatHeight = (float)g.intHeight;
+    const uint32_t numShapes = tile.shape_count;   // <= kWarpTableCap here
+    // strand counts -> exclusive scan (a handful of shapes per thread of the first warp)
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t mine[(kWarpTableCap + 31) / 32];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < (kWarpTableCap + 31) / 32; k++) {
+            const uint32_t i = (uint32_t)tid * ((kWarpTableCap + 31) / 32) + k;
+            mine[k] = i < numShapes ? __ldg(&P.shapes[tile.shape_start + i].num_strands) : 0u;
+            sum += mine[k];
+        }
+        uint32_t incl = sum;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (tid >= d) incl += v;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < (kWarpTableCap + 31) / 32; k++) {
+            const uint32_t i = (uint32_t)tid * ((kWarpTableCap + 31) / 32) + k;
+            if (i <= numShapes) S.shapeBase[i] = run;
+            run += mine[k];
+        }
+        if (tid == 31 && numShapes == (uint32_t)kWarpTableCap) S.shapeBase[kWarpTableCap] = run;
+    }
+    __syncthreads();
+    uint32_t shapeBegin = 0;
+    while (shapeBegin < numShapes) {
+        // the longest run of shapes whose strands fit the table (uniform across the CTA)
+        const uint32_t first = S.shapeBase[shapeBegin];
+        uint32_t shapeEnd = shapeBegin;
+        while (shapeEnd < numShapes && S.shapeBase[shapeEnd + 1] - first <= (uint32_t)kStrandTableCap) shapeEnd++;
+        if (shapeEnd == shapeBegin) {
+            // one shape with more strands than the table holds: every thread reads its headers itself
+            const uint4 rec = __ldg(reinterpret_cast<const uint4*>(P.shapes + tile.shape_start + shapeBegin));
+            const uint8_t* strand = P.geometry + 16ull * rec.z;
+            if (g.active && !t.failed) {
+                for (uint32_t k = 0; k < rec.w && !t.failed; k++) {
+                    const float4 h0 = __ldg(reinterpret_cast<const float4*>(strand));
+                    const float4 lc = __ldg(reinterpret_cast<const float4*>(strand + 16));
+                    const float2 yb = P.strandBounds ? __ldg(P.strandBounds + ((size_t)(strand - P.geometry) >> 4)) : make_float2(0.f, 0.f);
+                    const uint32_t sizeWord = __float_as_uint(h0.x);
+                    genStrand(P, q, t, ox, oy, floatHeight, shapeBegin | (k == 0 ? kEntryFirst : 0u) | (k + 1 == rec.w ? kEntryLast : 0u),
+                              sizeWord, strand, make_float2(h0.z, h0.w), lc, yb);
+                    strand += 8u * (sizeWord & 0xFFFFu);
+                }
+            }
+            shapeBegin += 1;
+            continue;
+        }
+        // stage: one thread per shape of the run
+        for (uint32_t i = shapeBegin + tid; i < shapeEnd; i += nThreads) {
+            const uint4 rec = __ldg(reinterpret_cast<const uint4*>(P.shapes + tile.shape_start + i));
+            const uint8_t* strand = P.geometry + 16ull * rec.z;
+            StrandEntry* e = S.entry + (S.shapeBase[i] - first);
+            for (uint32_t k = 0; k < rec.w; k++) {
+                const float4 h0 = __ldg(reinterpret_cast<const float4*>(strand));
+                e[k].lc = __ldg(reinterpret_cast<const float4*>(strand + 16));
+                e[k].right = make_float2(h0.z, h0.w);
+                const uint32_t off16 = (uint32_t)((size_t)(strand - P.geometry) >> 4);
+                e[k].yb = P.strandBounds ? __ldg(P.strandBounds + off16) : make_float2(0.f, 0.f);
+                e[k].sizeWord = __float_as_uint(h0.x);
+                e[k].offset16 = off16;
+                e[k].shapeAndFlags = i | (k == 0 ? kEntryFirst : 0u) | (k + 1 == rec.w ? kEntryLast : 0u);
+                strand += 8u * (__float_as_uint(h0.x) & 0xFFFFu);
+            }
+        }
+        __syncthreads();
+        const uint32_t nEntries = S.shapeBase[shapeEnd] - first;
+        if (g.active && !t.failed) {
+            // (a shape without strands has no entry: K.cl:1557-1592 does nothing for it either)
+            for (uint32_t k = 0; k < nEntries && !t.failed; k++) {
+                const StrandEntry& e = S.entry[k];
+                genStrand(P, q, t, ox, oy, floatHeight, e.shapeAndFlags, e.sizeWord, P.geometry + 16ull * e.offset16, e.right,
+                          e.lc, e.yb);
+            }
+        }
+        __syncthreads();
+        shapeBegin = shapeEnd;
+    }
 }
 
 // ---- sweep kernel body --------------------------------------------------------------------------------

@@ -2,7 +2,10 @@ import csv, subprocess, sys
 rep = sys.argv[1]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 0     # which kernel of the report (0-based)
+vals = rows[2 + which]
+print("# kernel:", vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?")
 keys = ["gpu__time_duration.sum","smsp__inst_executed.sum","smsp__thread_inst_executed_per_inst_executed.ratio","sm__warps_active.avg.pct_of_peak_sustained_active",
 "smsp__issue_active.avg.pct_of_peak_sustained_active","l1tex__t_sector_hit_rate.pct","lts__t_sector_hit_rate.pct","dram__bytes_read.sum","dram__bytes_write.sum",
 "launch__registers_per_thread","launch__occupancy_limit_registers","launch__occupancy_limit_shared_mem","launch__grid_size","launch__block_size","sm__maximum_warps_per_active_cycle_pct",
