@@ -50,7 +50,13 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
     extern __shared__ __align__(16) unsigned char smemRaw[];
 #endif
     TileStage& S = *reinterpret_cast<TileStage*>(smemRaw);
-    GenScratch* scratch = reinterpret_cast<GenScratch*>(smemRaw + ((sizeof(TileStage) + 15) & ~(size_t)15));
+    SearchSummaries R;
+    {
+        unsigned char* p = smemRaw + ((sizeof(TileStage) + 15) & ~(size_t)15);
+        R.yRange = reinterpret_cast<float2*>(p);
+        R.flags = reinterpret_cast<uint32_t*>(p + (size_t)kGenItems * 8);
+    }
+    GenScratch* scratch = reinterpret_cast<GenScratch*>(smemRaw + ((sizeof(TileStage) + 15) & ~(size_t)15) + searchSummariesBytes());
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     QueueCold<kQueueCap - kGenQueueHot> cold;
@@ -59,7 +65,6 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
     q.cold = &cold;
     q.thrHot = scratch[warp].qThr + lane;
     q.hdrHot = scratch[warp].qHdr + lane;
-    const int warpShift = P.computeDepth - 5;                    // warps per tile = threadsPerTile / 32
     const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
     unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkGenerate);
     for (;;) {
@@ -69,9 +74,8 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
         const int tileSlot = S.tileSlot;
         if (tileSlot >= nTiles) break;
         const int tileIndex = (int)P.tileOrder[tileBase + tileSlot];
-        const int column = (int)threadIdx.x;
-        const unsigned recUnit = ((unsigned)tileIndex << warpShift) + (unsigned)warp;   // thread records are indexed by tile, not by hand-out order
         const gudni_tile tile = P.tiles[tileIndex];
+        const int column = (int)threadIdx.x;   // the reference's thread number inside the tile
         const ThreadGeom g = threadGeom(P, tile, column);
         int generated = -1;
         int failed = 0;
@@ -79,19 +83,17 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
         if (tile.shape_count <= denseCap) {
             GenThread t;
             t.stack = ShapeStack{0ull, 0ull};
-            t.bits = 0u;
-            t.f = GenFlags{false, false};
-            t.enclosedByShape = false;
+            t.added = ShapeStack{0ull, 0ull};
             t.failed = false;
             q.init();
-            generateTileThresholds(P, S, q, t, tile, g);
-            failed = packWarp(P, q, g, t.stack, t.bits, t.failed, tileIndex, recUnit, column, generated, exhausted);
+            generateTileThresholds(P, S, R, q, t, tile, g);
+            failed = packWarp(P, q, g, t.stack, t.bits(), t.failed, tileIndex, column, generated, exhausted);
         } else {
             // a tile that stopped splitting at the 8-pixel floor with more shapes than stack bits:
             // its threads take the lane-private replay path (bit -> shape table, HBM queue)
             ThreadRec rec{};
             rec.count = kRecInactive;
-            P.threadRecs[(size_t)recUnit * 32 + lane] = rec;
+            P.threadRecs[((size_t)tileIndex << P.computeDepth) + (size_t)column] = rec;
             failed = g.active ? 1 : 0;
         }
         // statistics: thresholds of lanes that completed here (replayed lanes are counted by the replay)
@@ -414,14 +416,16 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     FrameParams P = frame;
     // occupancy of the persistent kernels on THIS context's device (a process may hold several contexts)
     const size_t sweepSmem = kSweepWarpsPerCta * sizeof(WarpScratch);
-    const size_t genSmem = ((sizeof(TileStage) + 15) & ~(size_t)15) + (size_t)(ctx->spec.threads_per_tile / 32) * sizeof(GenScratch);
+    const size_t genSmem = ((sizeof(TileStage) + 15) & ~(size_t)15) + searchSummariesBytes() +
+                           (size_t)(ctx->spec.threads_per_tile / 32) * sizeof(GenScratch);
     if (!ctx->occupancyKnown) {
         GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweepSmem));
         GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sweepCtasPerSm, raster_sweep_kernel,
                                                                           kSweepWarpsPerCta * 32, sweepSmem));
         // the attribute belongs to the function, not to the context: allow what the largest spec (1,024 threads per tile) needs
-        const size_t genSmemMax = ((sizeof(TileStage) + 15) & ~(size_t)15) + (size_t)32 * sizeof(GenScratch);
-        GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)genSmemMax));
+        const size_t genSmemMax = ((sizeof(TileStage) + 15) & ~(size_t)15) + searchSummariesBytes() + (size_t)32 * sizeof(GenScratch);
+        GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)std::min<size_t>(genSmemMax, (size_t)227 * 1024)));
         GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->genCtasPerSm, raster_generate_kernel,
                                                                           ctx->spec.threads_per_tile, genSmem));
         GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_slice_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

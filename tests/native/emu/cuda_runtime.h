@@ -250,11 +250,15 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
 inline int __float2int_rz(float f) { return f != f ? 0 : (f >= 2147483648.0f ? 2147483647 : (f <= -2147483648.0f ? (-2147483647 - 1) : (int)f)); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(long long v) { return __builtin_popcountll((unsigned long long)v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 template <class T> inline T atomicAdd(T* p, T v) { T old = *p; *p = (T)(old + v); return old; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline int min(int a, int b) { return a < b ? a : b; }
