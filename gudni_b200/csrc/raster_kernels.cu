@@ -1,5 +1,5 @@
-// raster_kernels.cu — the two raster kernels (fused generate+sort+sweep, and the HBM-queue replay
-// of spilled threads) and their launch wrappers.  Device arithmetic is in raster_device.cuh.
+// raster_kernels.cu — the raster kernels and their launch wrappers.  Device arithmetic is in raster_device.cuh
+// (per-column-thread functions shared with the replay), raster_warp.cuh (generate) and raster_split.cuh (render).
 #include "raster_kernels.cuh"
 
 #include <algorithm>
@@ -8,32 +8,28 @@
 
 using namespace gudni_dev;
 
-#ifndef GUDNI_SWEEP_WARPS
-#define GUDNI_SWEEP_WARPS 2
-#endif
 #ifndef GUDNI_SLICE_WARPS
 #define GUDNI_SLICE_WARPS 4
 #endif
 #ifndef GUDNI_COLOR_WARPS
 #define GUDNI_COLOR_WARPS 4
 #endif
-#ifndef GUDNI_SPLIT_SWEEP
-#define GUDNI_SPLIT_SWEEP 1     // 1: raster_slice_kernel + raster_color_kernel; 0: round 1's raster_sweep_kernel
-#endif
-constexpr int kSweepWarpsPerCta = GUDNI_SWEEP_WARPS;
 constexpr int kSliceWarpsPerCta = GUDNI_SLICE_WARPS;
 constexpr int kColorWarpsPerCta = GUDNI_COLOR_WARPS;
 
-// The frame is rasterized by two persistent kernels.  Both size their grid to what the chip holds
-// resident and every warp pulls (tile, 32-column group) units from a global counter until the frame
-// is done; the unit is the reference's work-group sliced by warps (`Work2D numTiles threadsPerTile`,
-// OpenCL/CallKernels.hs:141-142).
-//   raster_generate_kernel   generateThresholds + sortThresholds (K.cl:2030-2115): queues built and
-//                            sorted in shared memory, packed into HBM once (20 B per threshold)
-//   raster_sweep_kernel      renderThresholds (K.cl:2117-2167): substance table, colour cache,
-//                            pending list and the hot part of the queues in shared memory
-// Splitting them halves the instruction footprint each warp drags through the instruction cache
-// (one fused kernel saturated it) and lets each phase have the occupancy it needs.
+// A frame (or a launch of up to kLaunchTiles tiles of it) goes through six kernels on one stream; every one sizes
+// its grid to what the chip holds resident and pulls its work from a global counter, expensive tiles first:
+//   raster_generate_kernel    generateThresholds + sortThresholds (K.cl:2030-2115), one CTA per tile: sorted
+//                             threshold queues packed into HBM (20 B per threshold)
+//   raster_slice_kernel       the state machine of renderThresholds (K.cl:2117-2167) without colours: one
+//                             section stream per column-thread
+//   raster_resolve_kernel     the streams' shape stacks numbered (deduplicated per warp)
+//   raster_composite_kernel   every numbered stack composited once (determineColor, K.cl:1447-1513)
+//   raster_accumulate_kernel  colour * area per section, pixels stored
+//   raster_picture_kernel     tiles with picture substances: one pass, colours per pixel
+// and raster_spill_kernel replays, lane-privately against an HBM queue, the column-threads that did not fit the
+// on-chip structures.  Round 1 ran renderThresholds as one kernel; split this way each phase has the occupancy
+// and the lane utilisation it can reach (profiles/README.md).
 __device__ __forceinline__ void registerSpill(const FrameParams& P, int tileIndex, int column) {
     // replayed by raster_spill_kernel against an HBM queue of MAXTHRESHOLDS entries
     const unsigned long long slot = atomicAdd(&P.counters[kCntSpilled], 1ull);
@@ -102,49 +98,6 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
         if (lane == 0 && mine) atomicAdd(&P.counters[kCntThresholds], (unsigned long long)mine);
         if (exhausted) atomicAdd(&P.counters[kCntExhausted], 1ull);
         if (failed) registerSpill(P, tileIndex, column);
-    }
-}
-
-#ifndef GUDNI_SWEEP_MIN_CTAS
-#define GUDNI_SWEEP_MIN_CTAS 1
-#endif
-__global__ void __launch_bounds__(kSweepWarpsPerCta * 32, GUDNI_SWEEP_MIN_CTAS) raster_sweep_kernel(const FrameParams P, int tileBase, int nTiles) {
-#ifdef GUDNI_HOST_EMULATION
-    unsigned char* smemRaw = cuemu::dynamicShared;
-#else
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-#endif
-    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smemRaw);
-    const unsigned full = 0xffffffffu;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpScratch& W = scratch[warp];
-    LaneLog log;
-    LaneQueue q;
-    q.limit = min(kQueueCap, P.maxThresholds);
-    q.thrHot = W.qThr + lane;
-    q.hdrHot = W.qHdr + lane;
-    const int warpShift = P.computeDepth - 5;
-    const unsigned totalUnits = (unsigned)nTiles << warpShift;
-    const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
-    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkSweep);
-    for (;;) {
-        unsigned unit = 0;
-        if (lane == 0) unit = atomicAdd(workCounter, 1u);
-        unit = __shfl_sync(full, unit, 0);
-        if (unit >= totalUnits) break;
-        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> warpShift)];
-        const unsigned warpInTile = unit & ((1u << warpShift) - 1u);
-        const int column = (int)(warpInTile << 5) + lane;
-        const unsigned recUnit = ((unsigned)tileIndex << warpShift) + warpInTile;
-        const gudni_tile tile = P.tiles[tileIndex];
-        if (tile.shape_count > denseCap) continue;   // replayed lane-privately
-        const int failed = sweepWarp(P, W, q, log, tile, recUnit, column);
-        if (failed) {
-            // its thresholds were counted by the generate kernel; the replay counts them again
-            const ThreadRec rec = P.threadRecs[(size_t)recUnit * 32 + lane];
-            atomicAdd(&P.counters[kCntThresholds], 0ull - (unsigned long long)rec.count);
-            registerSpill(P, tileIndex, column);
-        }
     }
 }
 
@@ -415,13 +368,9 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     if (nTiles <= 0) return GUDNI_OK;
     FrameParams P = frame;
     // occupancy of the persistent kernels on THIS context's device (a process may hold several contexts)
-    const size_t sweepSmem = kSweepWarpsPerCta * sizeof(WarpScratch);
     const size_t genSmem = ((sizeof(TileStage) + 15) & ~(size_t)15) + searchSummariesBytes() +
                            (size_t)(ctx->spec.threads_per_tile / 32) * sizeof(GenScratch);
     if (!ctx->occupancyKnown) {
-        GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweepSmem));
-        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sweepCtasPerSm, raster_sweep_kernel,
-                                                                          kSweepWarpsPerCta * 32, sweepSmem));
         // the attribute belongs to the function, not to the context: allow what the largest spec (1,024 threads per tile) needs
         const size_t genSmemMax = ((sizeof(TileStage) + 15) & ~(size_t)15) + searchSummariesBytes() + (size_t)32 * sizeof(GenScratch);
         GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -444,7 +393,6 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
         ctx->accumulateCtasPerSm = std::max(ctx->accumulateCtasPerSm, 1);
         GUDNI_CUDA_TRY(ctx, cudaDeviceGetAttribute(&ctx->numSms, cudaDevAttrMultiProcessorCount, ctx->device));
         ctx->genCtasPerSm = std::max(ctx->genCtasPerSm, 1);
-        ctx->sweepCtasPerSm = std::max(ctx->sweepCtasPerSm, 1);
         ctx->sliceCtasPerSm = std::max(ctx->sliceCtasPerSm, 1);
         ctx->colorCtasPerSm = std::max(ctx->colorCtasPerSm, 1);
         ctx->occupancyKnown = true;
@@ -465,17 +413,12 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     ctx->launches++;
     raster_generate_kernel<<<std::min(ctx->genCtasPerSm * numSms, nTiles), ctx->spec.threads_per_tile, genSmem, ctx->stream>>>(P, tileBase, nTiles);
     ctx->launches++;
-#if GUDNI_SPLIT_SWEEP
     raster_slice_kernel<<<grid(ctx->sliceCtasPerSm, kSliceWarpsPerCta), kSliceWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
     raster_resolve_kernel<<<grid(ctx->resolveCtasPerSm, kResolveWarpsPerCta), kResolveWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
     raster_composite_kernel<<<ctx->compositeCtasPerSm * numSms, kCompositeWarpsPerCta * 32, 0, ctx->stream>>>(P);
     raster_accumulate_kernel<<<grid(ctx->accumulateCtasPerSm, kAccumulateWarpsPerCta), kAccumulateWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
     raster_picture_kernel<<<grid(ctx->colorCtasPerSm, kColorWarpsPerCta), kColorWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
     ctx->launches += 5;
-#else
-    raster_sweep_kernel<<<grid(ctx->sweepCtasPerSm, kSweepWarpsPerCta), kSweepWarpsPerCta * 32, sweepSmem, ctx->stream>>>(P, tileBase, nTiles);
-    ctx->launches++;
-#endif
     GUDNI_CUDA_TRY(ctx, cudaGetLastError());
     return GUDNI_OK;
 }

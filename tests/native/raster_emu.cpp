@@ -173,15 +173,11 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
                           static_cast<const uint8_t*>(boundsRecords), boundsStride, (int)nBoundsRecords, bounds.data(), counters.data());
         cuemu::launch(tile_order_kernel, dim3(1), dim3(256), tilesCopy.data(), 0, nTiles, order.data(), counters.data());
         cuemu::launch(raster_generate_kernel, dim3(2), dim3(in.spec->threads_per_tile), P, 0, nTiles);
-#if GUDNI_SPLIT_SWEEP
         cuemu::launch(raster_slice_kernel, dim3(2), dim3(kSliceWarpsPerCta * 32), P, 0, nTiles);
         cuemu::launch(raster_resolve_kernel, dim3(2), dim3(kResolveWarpsPerCta * 32), P, 0, nTiles);
         cuemu::launch(raster_composite_kernel, dim3(2), dim3(kCompositeWarpsPerCta * 32), P);
         cuemu::launch(raster_accumulate_kernel, dim3(2), dim3(kAccumulateWarpsPerCta * 32), P, 0, nTiles);
         cuemu::launch(raster_picture_kernel, dim3(2), dim3(kColorWarpsPerCta * 32), P, 0, nTiles);
-#else
-        cuemu::launch(raster_sweep_kernel, dim3(2), dim3(kSweepWarpsPerCta * 32), P, 0, nTiles);
-#endif
         cuemu::launch(raster_spill_kernel, dim3(1), dim3(spillSlots), P, spillThr.data(), spillHdr.data(), spillSlots);
     }
     (void)nShapes;

@@ -353,11 +353,12 @@ def test_shared_reciprocal_division(emu):
         emu.raster_emu_set_rcp_error(0)
 
 
-def test_kernel_variant_unpaired_colour_loop():
-    """A compile-time variant checked the same way (-DGUDNI_EVAL_PAIR=0: one stack per lane in the colour
-    evaluation, the loop the default build does not contain) — what tools/variants.sh builds for the GPU can be
-    held to the oracle here first."""
-    L = ctypes.CDLL(_build.build_raster_emu(extra=("-DGUDNI_EVAL_PAIR=0",), suffix="_evalpair0"))
+def test_kernel_variant_small_tables():
+    """A compile-time variant checked the same way (a 64-line stack cache in the resolve kernel, small chunks of
+    strands and (strand, column) pairs in the generate kernel: every eviction and chunk-boundary path runs on small
+    scenes) — what tools/variants.sh builds for the GPU can be held to the oracle here first."""
+    L = ctypes.CDLL(_build.build_raster_emu(extra=("-DGUDNI_COLOR_LINES=64", "-DGUDNI_STRAND_TABLE=8", "-DGUDNI_GEN_ITEMS=256"),
+                                            suffix="_small"))
     c = ctypes
     L.raster_emu_frame.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int,
                                    c.POINTER(CSpec), c.c_void_p, c.c_int64, c.c_void_p, c.c_void_p, c.c_int, c.c_int64,
