@@ -218,9 +218,12 @@ __global__ void __launch_bounds__(kCompositeWarpsPerCta * 32) raster_composite_k
 
 // The resolved streams with the colours at hand: accumulation and pixel stores.
 __global__ void __launch_bounds__(kAccumulateWarpsPerCta * 32) raster_accumulate_kernel(const FrameParams P, int tileBase, int nTiles) {
+    __shared__ AccumScratch scratch[kAccumulateWarpsPerCta];
+    AccumScratch& W = scratch[threadIdx.x >> 5];
     forEachUnit(P, tileBase, nTiles, kCntWorkAccumulate, [&](int, const gudni_tile& tile, unsigned recUnit, int column) {
         if (tileHasPictures(P, tile)) return;
-        accumulateWarp(P, tile, recUnit, column);
+        accumulateWarp(P, W, tile, recUnit, column);
+        __syncwarp();
     });
 }
 

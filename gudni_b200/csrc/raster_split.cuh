@@ -530,24 +530,40 @@ __device__ __forceinline__ void storePixels(const FrameParams& P, uint32_t* outp
 
 // One warp, one (tile, 32-column group) of a dense tile without pictures: the resolved streams again, now with
 // the colours at hand.
-__device__ __forceinline__ void accumulateWarp(const FrameParams& P, const gudni_tile& tile, unsigned unit, int column) {
+//
+// Pixel stores.  A lane finishes the pixels of its column at its own pace (a column the shapes leave alone is a
+// few PEND records, each standing for a run of rows; its neighbour may cross an outline and need dozens of
+// sections for the same rows), and 32 lanes storing 4 bytes each to 32 different rows is 32 partial sectors.  So
+// finished pixels first go into a window of kRowWindow rows x 32 columns in shared memory — every lane only ever
+// touches its own column of it — and a row leaves for memory when every lane has produced it: one 128-byte
+// store per row.  A lane that gets kRowWindow rows ahead of the slowest one waits.
+#ifndef GUDNI_ROW_WINDOW
+#define GUDNI_ROW_WINDOW 16
+#endif
+constexpr int kRowWindow = GUDNI_ROW_WINDOW;   // power of two
+struct AccumScratch {
+    uint32_t rows[kRowWindow][32];
+};
+__device__ __forceinline__ void accumulateWarp(const FrameParams& P, AccumScratch& W, const gudni_tile& tile, unsigned unit, int column) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const ThreadGeom g = threadGeom(P, tile, column);
     const ThreadRec rec = P.threadRecs[(size_t)unit * 32 + lane];
     uint32_t* outp = P.out + (size_t)(g.originY - P.rowOrigin) * P.width + g.originX;   // only dereferenced when active
-    bool done = rec.count == kRecInactive;
+    const bool mine = rec.count != kRecInactive;
+    bool done = !mine;
     StreamReader in;
     in.chunk = P.streamPool; in.pos = 0; in.pair = make_uint4(0u, 0u, 0u, 0u);
-    if (!done) in.open(P.streamPool, rec.chunk);
+    if (mine) in.open(P.streamPool, rec.chunk);
     float accR = 0.f, accG = 0.f, accB = 0.f, accArea = 0.f;
-    int wrow = 0;
-    // Two alternating phases so that the lanes run the same code: (1) every lane adds up the sections of its
-    // current pixel — a short loop of a few instructions per section; (2) the lanes that finished a pixel
-    // convert and store it together (three divisions and the stores: K.cl:1853-1862).
+    int wrow = 0;             // rows this lane has produced (into the window)
+    int flushed = 0;          // rows already stored (warp-uniform)
+    uint32_t pendWord = 0u;   // a finished pixel and the rows it still has to fill
+    int pendRep = 0;
     for (;;) {
+        // (1) every lane adds up the sections of its current pixel — a few instructions per section
         int rep = 0;
-        while (!done && rep == 0) {
+        while (!done && pendRep == 0 && rep == 0) {
             const uint2 r = in.get();
             const uint32_t kind = r.x & kRecKindMask;
             if (kind == kRecLink) {
@@ -570,11 +586,31 @@ __device__ __forceinline__ void accumulateWarp(const FrameParams& P, const gudni
             }
         }
         __syncwarp();
+        // (2) the lanes that finished a pixel convert it together (three divisions: K.cl:1853-1862)
         if (rep) {
-            storePixels(P, outp, wrow, rep, accR, accG, accB, accArea);
+            pendWord = pixelWord(accR, accG, accB, accArea);
+            pendRep = rep;
             accR = accG = accB = accArea = 0.f;
         }
-        if (!__any_sync(full, !done)) break;
+        // (3) ... and put it into their column of the window, as far as the window reaches
+        if (pendRep) {
+            const int n = min(pendRep, flushed + kRowWindow - wrow);
+            for (int k = 0; k < n; k++) W.rows[(wrow + k) & (kRowWindow - 1)][lane] = pendWord;
+            wrow += n;
+            pendRep -= n;
+        }
+        // (4) rows every unfinished lane has produced leave as whole rows
+        const bool finished = done && pendRep == 0;
+        int lo = finished ? 0x7FFFFFFF : wrow, hi = mine ? wrow : 0;
+        for (int d = 16; d > 0; d >>= 1) {
+            lo = min(lo, __shfl_xor_sync(full, lo, d));
+            hi = max(hi, __shfl_xor_sync(full, hi, d));
+        }
+        const int upTo = min(lo, hi);
+        for (int r = flushed; r < upTo; r++)
+            if (mine && r < wrow) outp[(size_t)r * P.width] = W.rows[r & (kRowWindow - 1)][lane];
+        flushed = upTo;
+        if (lo == 0x7FFFFFFF) break;   // every lane finished, and what they produced has just been stored
     }
 }
 

@@ -177,7 +177,10 @@ __device__ __forceinline__ void generateTileThresholds(const FrameParams& P, Til
     const float ox = (float)g.originX, oy = (float)g.originY, floatHeight = (float)g.intHeight;
     const int tileWidth = 1 << tile.h_depth;
     const int column = tid & (tileWidth - 1);
-    const uint32_t chunkCap = (uint32_t)max(1, min(kStrandTableCap, kGenItems >> tile.h_depth));
+    // A tile of one or two slabs has nothing to share: its threads run down the staged headers on their own
+    // (strandThresholds: search, classify, spawn per strand), a whole table of strands between two barriers.
+    const bool shareSearches = (nThreads >> tile.h_depth) > 2;
+    const uint32_t chunkCap = shareSearches ? (uint32_t)max(1, min(kStrandTableCap, kGenItems >> tile.h_depth)) : (uint32_t)kStrandTableCap;
     const bool haveBounds = P.strandBounds != nullptr;
     const float below = floatHeight + kCullMargin;
     const uint32_t numShapes = tile.shape_count;   // <= kWarpTableCap here
@@ -253,6 +256,21 @@ __device__ __forceinline__ void generateTileThresholds(const FrameParams& P, Til
         }
         __syncthreads();
         const int count = (int)(S.shapeBase[shapeEnd] - first);
+        if (!shareSearches) {
+            if (g.active && !t.failed) {
+                for (int k = 0; k < count; k++) {
+                    const StrandEntry& en = S.entry[k];
+                    GenFlags f{false, false};
+                    strandThresholds(q, P.geometry + 16ull * en.offset16, en.sizeWord, ox, oy, floatHeight, en.shapeAndFlags & kEntryShapeMask,
+                                     f, en.right, en.lc, haveBounds, en.yb);
+                    if (q.failed()) { t.failed = true; break; }
+                    t.note(en.shapeAndFlags & kEntryShapeMask, f);
+                }
+            }
+            __syncthreads();
+            shapeBegin = shapeEnd;
+            continue;
+        }
         // ---- A: the chunk's (strand, column) pairs, shared out over the CTA ----------------------------------
         for (int item = tid; item < count * tileWidth; item += nThreads) {
             const StrandEntry& en = S.entry[item >> tile.h_depth];
