@@ -108,6 +108,22 @@ def cpu_kind():
     return "reference" if oracle.reference_lib() is not None else "port"
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms are meant to use every host core, so the
+    OpenMP pools of the oracle and of the compiled reference kernels are sized explicitly."""
+    from oracle import oracle
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except (AttributeError, OSError):
+        pass
+    oracle.lib().gudni_oracle_set_threads(n)
+    ref = oracle.reference_lib()
+    if ref is not None:
+        ref.gudni_ref_set_threads(n)
+    return n
+
+
 def oracle_frame_sampler(scene, budget_s=12.0, kind=None):
     """Returns f() -> (seconds per FULL frame, sample description).  Frames that would take longer
     than `budget_s` are sampled: the tile tree is built for the whole scene, then an evenly spread
@@ -138,6 +154,8 @@ def oracle_frame_sampler(scene, budget_s=12.0, kind=None):
         t2 = time.perf_counter()
         return (t1 - t0) + (t2 - t1) * len(js) / len(sel)
 
+    run.sampled = stride > 1
+    run.est_seconds = est / stride if stride > 1 else est     # wall clock of one sampled step
     return run, desc
 
 
@@ -235,20 +253,29 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import oracle
+    cores = use_all_host_cores()
     scene = make_scene(args.workload)
-    # keep the whole --steps/--warmup run within a few minutes on the host cores
-    budget = float(np.clip(150.0 / (args.steps + 1), 2.0, 12.0))
     kind = cpu_kind()
+    # The whole --steps/--warmup run has to end within a few minutes on the host cores: a step is one frame, or —
+    # when a frame takes longer than the per-step budget — a bounded sample of its raster jobs scaled to the frame
+    # ("sampled": true).  At most `max_steps` steps are timed however many were asked for; "steps" reports what ran.
+    total_budget = 150.0
+    budget = float(np.clip(total_budget / (args.steps + 1), 2.0, 12.0))
     run, desc = oracle_frame_sampler(scene, budget_s=budget, kind=kind)
-    for _ in range(min(args.warmup, 1)):
+    max_steps = max(1, int(total_budget / max(run.est_seconds, 1e-3)) - 1)
+    steps = max(1, min(args.steps, max_steps))
+    warmup = min(args.warmup, 1)
+    for _ in range(warmup):
         run()
-    times = [run() for _ in range(args.steps)]
+    t_wall = time.perf_counter()
+    times = [run() for _ in range(steps)]
+    t_wall = time.perf_counter() - t_wall
     t = float(np.mean(times))
-    cores = oracle.host_threads()
     value = 1.0 / t
     line = {
         "impl": "reference", "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True,
+        "steps": steps, "steps_requested": args.steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "sampled": bool(run.sampled), "wall_seconds_timed": t_wall,
         "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][1], "canvas": [scene.width, scene.height],
                    "spec": "G=256 MAXT=1024 maxStrandsPerTile=1022 MAXSHAPE=127"},
@@ -438,6 +465,17 @@ def run_native(args, rank, world, local_rank):
             e2e_times.append(time.perf_counter() - t0)
     for a in pinned:
         r.host_unregister(a)
+    # the same call with the caller's buffers left pageable (what an unmodified Haskell caller has: SURVEY.md §8(b))
+    e2e_pageable = None
+    if world == 1:
+        tp = []
+        for i in range(2 + n_e2e):
+            t0 = time.perf_counter()
+            r.raster_scene(i, scene, out=host_img)
+            if i >= 2:
+                tp.append(time.perf_counter() - t0)
+        e2e_pageable = {"value": 1.0 / float(np.mean(tp)), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "buffers": "pageable host memory (no cudaHostRegister)"}
     t_e2e = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -472,15 +510,17 @@ def run_native(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": 1.0 / float(t_e2e.item()), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
+            "e2e_pageable": e2e_pageable,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "raster_generate_kernel + raster_sweep_kernel (+ raster_spill_kernel), one launch each per frame", "kernel_ms": k_ms,
+                         "kernel": "the frame's raster kernels, one launch each: raster_generate_kernel, raster_slice_kernel, "
+                                   "raster_resolve_kernel, raster_composite_kernel, raster_accumulate_kernel "
+                                   "(+ raster_picture_kernel, raster_spill_kernel)", "kernel_ms": k_ms,
                          "bin_ms": float(np.mean(bin_ms)) if bin_ms else None, "algorithmic_bytes": int(a_bytes),
                          "note": "the path is instruction-issue / latency bound, not bandwidth bound: per S4 frame 14.1 M "
-                                 "thresholds of curve subdivision, 75 M sweep sections, 16 M stack composites of ~38 layers; "
-                                 "ncu (profiles/r1_sweep_summary.txt, r1_generate_summary.txt): sweep 49 % issue utilisation "
-                                 "at 3.0 warps/scheduler, generate 78 %; DRAM traffic 1.9 GB/frame = 0.3 ms at peak"},
+                                 "thresholds of curve subdivision, 75 M sweep sections, 15.7 M stack composites of ~38 layers; "
+                                 "ncu per kernel in profiles/r2_*_summary.txt"},
             "frame": stats.as_dict() if stats is not None else None,
         }
         if per_rank is not None:
@@ -509,12 +549,32 @@ def run_native(args, rank, world, local_rank):
                                     "mpixel_per_s": sb.width * sb.height * 1e3 / float(np.mean(tb)) / 1e6}}
             sr.close(); db.free()
         if world == 1 and args.workload == "S4" and not args.no_also:
+            # the multi-GPU workload on ONE GPU, so that the 1 -> 8 curve of the scaling run can be read on one workload
+            s5 = make_scene("S5")
+            sr = StripRenderer(r, s5, 0, 1, None)
+            d5 = DeviceScene(r, s5)
+            for i in range(3):
+                sr.render(i, d5)
+            t5 = []
+            for i in range(5):
+                flush.fill_(i & 0xFF)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); sr.render(3 + i, d5); e1.record(stream)
+                torch.cuda.synchronize()
+                t5.append(e0.elapsed_time(e1))
+            line["also"]["S5_single_gpu"] = {"workload": WORKLOADS["S5"][1], "value": 1e3 / float(np.mean(t5)), "unit": "frames/s",
+                                             "ms_per_step": float(np.mean(t5)),
+                                             "mpixel_per_s": s5.width * s5.height * 1e3 / float(np.mean(t5)) / 1e6}
+            sr.close(); d5.free(); del sr, s5
+        if world == 1 and args.workload == "S4" and not args.no_also:
             try:
                 line["also"]["level3_outlines_in"] = level3_reading(r, scene, dscene, stream, flush, torch)
             except Exception as e:  # noqa: BLE001 - a secondary reading never fails the bench
                 line["also"]["level3_outlines_in"] = {"unavailable": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle
+            use_all_host_cores()
             kind = cpu_kind()
             run, desc = oracle_frame_sampler(scene, budget_s=10.0, kind=kind)
             t = float(np.mean([run() for _ in range(2)]))

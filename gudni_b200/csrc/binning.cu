@@ -195,10 +195,15 @@ __global__ void __launch_bounds__(256) bin_subdivide(const BinParams P) {
     BinNode* cur = P.frontier + (size_t)root * 2 * P.maxNodes;
     BinNode* nxt = cur + P.maxNodes;
     uint32_t side = 0;
-    if (!rootActive(P, rty) || P.counters[kOverflow]) {
+    // Another CTA may raise the overflow flag at any moment (arena cursor check below): one thread reads it and the
+    // CTA branches on the shared copy, so that its threads leave together or not at all.
+    if (threadIdx.x == 0) sAbort = (!rootActive(P, rty) || P.counters[kOverflow]) ? 1u : 0u;
+    __syncthreads();
+    if (sAbort) {
         if (threadIdx.x == 0) { P.leafCount[root] = 0; P.refCount[root] = 0; P.rootCursor[root] = 0; }
         return;
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
         BinNode n{};
         n.hDepth = n.vDepth = (uint8_t)P.rootDepth;

@@ -296,15 +296,21 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(gudni_tile* __restrict
 
 // (min y, max y) over all points of every strand of `count` shape records (`stride` bytes apart, each
 // starting with {u64 tag, u32 geo_start, u32 num_strands}); strand layout K.cl:1365-1376.
-__global__ void strand_bounds_kernel(const uint8_t* __restrict__ geometry, const uint8_t* __restrict__ records, int stride,
-                                     int count, float2* __restrict__ bounds, unsigned long long* __restrict__ counters) {
+__global__ void strand_bounds_kernel(const uint8_t* __restrict__ geometry, size_t geometryBytes, const uint8_t* __restrict__ records,
+                                     int stride, int count, float2* __restrict__ bounds, unsigned long long* __restrict__ counters) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    bool infinite = false;
+    bool infinite = false, outside = false;
     const uint4 rec = __ldg(reinterpret_cast<const uint4*>(records + (size_t)i * stride));
-    const uint8_t* strand = geometry + 16ull * rec.z;
+    // The raster kernels trust geo_start, the strand count and the size words: this is the one place every strand
+    // header is read before them, so a record that points outside the heap is caught here (and the frame defused
+    // like one with an infinite coordinate: tile_order_kernel) instead of being walked.
+    size_t at = 16ull * rec.z;
     for (uint32_t s = 0; s < rec.w; s++) {
+        if (at + 32 > geometryBytes) { outside = true; break; }
+        const uint8_t* strand = geometry + at;
         const uint32_t size = __ldg(reinterpret_cast<const uint32_t*>(strand)) & 0xFFFFu;   // in 8-byte units
+        if (size < 4u || (size & 1u) || at + 8ull * size > geometryBytes) { outside = true; break; }   // 16-byte records: K.cl:1365-1376
         float lo = FLT_MAX, hi = -FLT_MAX;
         for (uint32_t k = 1; k < size; k++) {
             const float2 p = __ldg(reinterpret_cast<const float2*>(strand + 8 * k));
@@ -312,10 +318,11 @@ __global__ void strand_bounds_kernel(const uint8_t* __restrict__ geometry, const
             hi = fmaxf(hi, p.y);
             infinite |= fabsf(p.x) == INFINITY || fabsf(p.y) == INFINITY;   // NaN terminates (and compares false)
         }
-        bounds[(size_t)(strand - geometry) >> 4] = make_float2(lo, hi);
-        strand += 8u * size;
+        bounds[at >> 4] = make_float2(lo, hi);
+        at += 8ull * size;
     }
-    if (infinite) counters[kCntNonFinite] = 1ull;
+    if (infinite) atomicOr(&counters[kCntNonFinite], 1ull);
+    if (outside) atomicOr(&counters[kCntNonFinite], 2ull);
 }
 
 // div3 against the compiler's IEEE division on pseudo-random operands (and the edge cases around
@@ -354,7 +361,7 @@ namespace gudni_launch {
 int strandBounds(gudni_ctx* ctx, const void* geometry, const void* records, int stride, int count, float2* bounds) {
     if (count <= 0) return GUDNI_OK;
     unsigned long long* counters = ctx->counters.as<unsigned long long>();
-    strand_bounds_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(geometry),
+    strand_bounds_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(geometry), ctx->geometryBytes,
                                                                      static_cast<const uint8_t*>(records), stride, count, bounds, counters);
     ctx->launches++;
     GUDNI_CUDA_TRY(ctx, cudaGetLastError());

@@ -518,6 +518,8 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     fprintf(stderr, "[stats] records %llu ready-hits %llu pending-hits %llu new %llu slow %llu rounds %llu flushes %llu logged %llu\n",
             counters[8], counters[9], counters[10], counters[11], counters[12], counters[13], counters[14], counters[15]);
 #endif
+    if (counters[gudni_dev::kCntNonFinite] & 2ull)
+        return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "a shape's strands run outside the geometry heap (geo_start, strand count or a strand's size word): nothing was rasterized");
     if (counters[gudni_dev::kCntNonFinite])
         return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "geometry holds a point at infinity: the reference's curve bisection does not terminate on it; nothing was rasterized");
     if (binCounters[4])

@@ -169,7 +169,7 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
     if (dbgShapeBits) for (int64_t i = 0; i < nColumns; i++) dbgShapeBits[i] = -1;
     if (nTiles > 0) {
         if (nBoundsRecords > 0)
-            cuemu::launch(strand_bounds_kernel, dim3((unsigned)((nBoundsRecords + 255) / 256)), dim3(256), P.geometry,
+            cuemu::launch(strand_bounds_kernel, dim3((unsigned)((nBoundsRecords + 255) / 256)), dim3(256), P.geometry, in.geometryBytes,
                           static_cast<const uint8_t*>(boundsRecords), boundsStride, (int)nBoundsRecords, bounds.data(), counters.data());
         cuemu::launch(tile_order_kernel, dim3(1), dim3(256), tilesCopy.data(), 0, nTiles, order.data(), counters.data());
         cuemu::launch(raster_generate_kernel, dim3(2), dim3(in.spec->threads_per_tile), P, 0, nTiles);

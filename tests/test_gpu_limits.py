@@ -77,3 +77,27 @@ def test_argument_validation(rasterizer):
     rasterizer.frame_end(want_image=False)
     with pytest.raises(GudniError):
         setup_rasterizer(spec=RasterSpec(threads_per_tile=100))   # not a power of two
+
+
+def test_records_that_leave_the_geometry_heap_are_refused(rasterizer):
+    """A shape record whose strands run past the geometry heap is refused with GUDNI_ERR_ARGUMENT (caught by
+    strand_bounds_kernel before any raster kernel walks it); the context stays usable."""
+    import numpy as np
+    from gudni_b200 import scenes
+    from gudni_b200.raster import GudniError
+    from oracle import oracle
+    scene = scenes.medium_square()
+    good = oracle.render(scene, taps=False)
+    bad = scenes.medium_square()
+    bad.entries = bad.entries.copy()
+    bad.entries["geo_start"] = len(bad.geometry) // 16 + 1000
+    with pytest.raises(GudniError) as e:
+        rasterizer.raster_scene(0, bad)
+    assert e.value.code == -1 and "geometry heap" in str(e.value)
+    bad2 = scenes.medium_square()
+    bad2.geometry = bad2.geometry.copy()
+    bad2.geometry.view(np.uint16)[0] = 0x7FF0        # a size word that runs far past the heap
+    with pytest.raises(GudniError):
+        rasterizer.raster_scene(0, bad2)
+    img, stats = rasterizer.raster_scene(1, scene)
+    assert np.array_equal(img, good.image)

@@ -102,6 +102,27 @@ def test_infinite_coordinate_is_refused_not_rasterized(emu, value, coord):
     assert (counts[counts >= 0] == 0).all()            # background only: no thread generated a threshold
 
 
+@pytest.mark.parametrize("what", ["geo_start", "size_word", "odd_size"])
+def test_records_that_leave_the_geometry_heap_are_refused(emu, what):
+    """geo_start, the strand count and the strands' size words come from the caller; strand_bounds_kernel walks every
+    strand header before the raster kernels do, flags a record that leaves the heap (or a size that is not whole
+    16-byte records) and the frame is defused like one with an infinite coordinate — no out-of-bounds read."""
+    scene = scenes.medium_square()
+    jobs = oracle.build_raster_jobs(scene)
+    if what == "geo_start":
+        for job in jobs:
+            job.shapes = job.shapes.copy()
+            job.shapes["geo_start"] = len(scene.geometry) // 16 + 1000
+    else:
+        scene.geometry = scene.geometry.copy()
+        words = scene.geometry.view(np.uint16)
+        words[0] = 0x7FF0 if what == "size_word" else words[0] + 1
+    rc, out, counts, bits, stats = emulate_frame(emu, scene, jobs)
+    assert rc == 0
+    assert (stats[4] & 2) and stats[0] == 0
+    assert (counts[counts >= 0] == 0).all()
+
+
 def test_nan_and_huge_coordinates_still_rasterize(emu):
     """NaN and finite values up to 3e38 terminate in the reference, so they are not refused (bits equal the oracle's)."""
     for value in (np.nan, 3.0e38, -3.0e38):
