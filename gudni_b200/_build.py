@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # parity contract with the oracle: IEEE f32, no FMA contraction, IEEE division / sqrt
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
 ]
 
 

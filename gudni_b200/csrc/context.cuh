@@ -16,6 +16,9 @@
 struct DevBuf {
     void* ptr = nullptr;
     size_t cap = 0;
+    // input cache (gudni_b200_frame_begin_cached): what the buffer holds, as the caller named it
+    uint64_t generation = 0;
+    size_t bytesHeld = 0;
     template <class T>
     T* as() const { return static_cast<T*>(ptr); }
 };
@@ -72,6 +75,7 @@ struct gudni_ctx {
     unsigned long long refCapSlabs = 0;
     unsigned long long refDemand = 0;          // slabs of stack numbers drawn last frame
     int spillSlots = 0;
+    int64_t uploadsSkipped = 0;           // input-cache hits (gudni_b200_frame_begin_cached)
     int64_t retriedFrames = 0;            // frames rasterized twice because a per-frame buffer was undersized
 
     // taps

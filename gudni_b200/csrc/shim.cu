@@ -138,9 +138,16 @@ int beginFrameCommon(gudni_ctx* ctx, const float bg[4], int width, int height, i
     return GUDNI_OK;
 }
 
-int uploadTo(gudni_ctx* ctx, DevBuf& buf, const void* src, size_t bytes) {
+// `generation` != 0: skip the copy if the buffer already holds `bytes` bytes uploaded under that generation
+int uploadTo(gudni_ctx* ctx, DevBuf& buf, const void* src, size_t bytes, uint64_t generation = 0) {
+    if (generation != 0 && buf.ptr && buf.generation == generation && buf.bytesHeld == bytes) {
+        ctx->uploadsSkipped++;
+        return GUDNI_OK;
+    }
     GUDNI_TRY(devEnsure(ctx, buf, std::max<size_t>(bytes, 16)));
     if (bytes) GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(buf.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    buf.generation = generation;
+    buf.bytesHeld = bytes;
     return GUDNI_OK;
 }
 
@@ -221,22 +228,24 @@ void gudni_b200_destroy(gudni_ctx* ctx) {
 const char* gudni_b200_last_error(gudni_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 // queueRasterJobs' frame-constant uploads, OpenCL/CallKernels.hs:229-235
-int gudni_b200_frame_begin(gudni_ctx* ctx, const void* geometry, size_t geometry_bytes, const float* substances,
-                           int n_substances, const uint8_t* picture_bytes, size_t n_picture_bytes,
-                           const gudni_picture_use* picture_uses, int n_picture_uses, const float background_rgba[4],
-                           int width, int height, int frame_number) {
+int gudni_b200_frame_begin_cached(gudni_ctx* ctx, const void* geometry, size_t geometry_bytes, const float* substances,
+                                  int n_substances, const uint8_t* picture_bytes, size_t n_picture_bytes,
+                                  const gudni_picture_use* picture_uses, int n_picture_uses, const float background_rgba[4],
+                                  int width, int height, int frame_number, const gudni_generations* gen) {
     if (!ctx) return GUDNI_ERR_ARGUMENT;
     if ((geometry_bytes && !geometry) || (n_substances && !substances) || (n_picture_bytes && !picture_bytes) ||
         (n_picture_uses && !picture_uses) || !background_rgba || n_substances < 0 || n_picture_uses < 0)
         return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "frame_begin: null or negative-sized input");
     if (n_substances >= (1 << 30)) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "frame_begin: more than 2^30 substances");
+    const gudni_generations none{};
+    if (!gen) gen = &none;
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evFrameBegin, ctx->stream));
     GUDNI_TRY(beginFrameCommon(ctx, background_rgba, width, height, frame_number));
-    GUDNI_TRY(uploadTo(ctx, ctx->geometry, geometry, geometry_bytes));
-    GUDNI_TRY(uploadTo(ctx, ctx->substances, substances, (size_t)n_substances * 16));
-    GUDNI_TRY(uploadTo(ctx, ctx->pictures, picture_bytes, n_picture_bytes));
-    GUDNI_TRY(uploadTo(ctx, ctx->pictureUses, picture_uses, (size_t)n_picture_uses * sizeof(gudni_picture_use)));
+    GUDNI_TRY(uploadTo(ctx, ctx->geometry, geometry, geometry_bytes, gen->geometry));
+    GUDNI_TRY(uploadTo(ctx, ctx->substances, substances, (size_t)n_substances * 16, gen->substances));
+    GUDNI_TRY(uploadTo(ctx, ctx->pictures, picture_bytes, n_picture_bytes, gen->pictures));
+    GUDNI_TRY(uploadTo(ctx, ctx->pictureUses, picture_uses, (size_t)n_picture_uses * sizeof(gudni_picture_use), gen->picture_uses));
     ctx->geometryPtr = ctx->geometry.ptr;
     ctx->substancesPtr = ctx->substances.ptr;
     ctx->picturesPtr = ctx->pictures.ptr;
@@ -247,6 +256,14 @@ int gudni_b200_frame_begin(gudni_ctx* ctx, const void* geometry, size_t geometry
     ctx->nPictureUses = n_picture_uses;
     GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evUploadDone, ctx->stream));
     return GUDNI_OK;
+}
+
+int gudni_b200_frame_begin(gudni_ctx* ctx, const void* geometry, size_t geometry_bytes, const float* substances,
+                           int n_substances, const uint8_t* picture_bytes, size_t n_picture_bytes,
+                           const gudni_picture_use* picture_uses, int n_picture_uses, const float background_rgba[4],
+                           int width, int height, int frame_number) {
+    return gudni_b200_frame_begin_cached(ctx, geometry, geometry_bytes, substances, n_substances, picture_bytes, n_picture_bytes,
+                                         picture_uses, n_picture_uses, background_rgba, width, height, frame_number, nullptr);
 }
 
 int gudni_b200_frame_begin_device(gudni_ctx* ctx, const void* dev_geometry, size_t geometry_bytes,
@@ -365,14 +382,17 @@ static int rasterSceneCommon(gudni_ctx* ctx, const void* devEntries, int n_entri
 }
 
 // buildTileTree/addShapeToTree + buildRasterJobs + the job loop of queueRasterJobs
-int gudni_b200_raster_scene(gudni_ctx* ctx, const gudni_shape_entry* entries, int n_entries) {
+int gudni_b200_raster_scene_cached(gudni_ctx* ctx, const gudni_shape_entry* entries, int n_entries, uint64_t generation) {
     if (!ctx) return GUDNI_ERR_ARGUMENT;
     if (!ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_scene outside a frame");
     if (ctx->nTiles) return ctxFail(ctx, GUDNI_ERR_STATE, "raster_scene after other raster calls of the frame");
     if (n_entries < 0 || (n_entries && !entries)) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "raster_scene: bad entries");
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    GUDNI_TRY(uploadTo(ctx, ctx->entries, entries, (size_t)n_entries * sizeof(gudni_shape_entry)));
+    GUDNI_TRY(uploadTo(ctx, ctx->entries, entries, (size_t)n_entries * sizeof(gudni_shape_entry), generation));
     return rasterSceneCommon(ctx, ctx->entries.ptr, n_entries);
+}
+int gudni_b200_raster_scene(gudni_ctx* ctx, const gudni_shape_entry* entries, int n_entries) {
+    return gudni_b200_raster_scene_cached(ctx, entries, n_entries, 0);
 }
 
 int gudni_b200_raster_scene_device(gudni_ctx* ctx, const void* dev_entries, int n_entries) {

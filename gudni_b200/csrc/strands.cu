@@ -171,6 +171,7 @@ int buildStrands(gudni_ctx* ctx, const void* devShapes, int nShapes, const void*
     ctx->builtStrands = 0;
     // the later stages take these pointers even when there is nothing behind them
     GUDNI_TRY(devEnsure(ctx, ctx->geometry, 16));
+    ctx->geometry.generation = ctx->entries.generation = 0;   // what the input cache knew about these buffers is gone
     GUDNI_TRY(devEnsure(ctx, ctx->entries, 32));
     ctx->geometryPtr = ctx->geometry.ptr;
     if (nShapes == 0) return GUDNI_OK;

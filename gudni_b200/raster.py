@@ -32,6 +32,9 @@ ABI_SYMBOLS = [
     "gudni_b200_debug_strands", "gudni_b200_sync", "gudni_b200_last_frame_ms", "gudni_b200_launch_count",
     "gudni_b200_set_stream", "gudni_b200_debug_selftest", "gudni_b200_debug_enable", "gudni_b200_debug_thread_counts", "gudni_b200_debug_binned",
     "gudni_b200_last_error", "gudni_b200_destroy",
+    "gudni_b200_frame_begin_cached", "gudni_b200_raster_scene_cached",
+    "gudni_b200_multi_init", "gudni_b200_multi_destroy", "gudni_b200_multi_last_error", "gudni_b200_multi_set_presenting",
+    "gudni_b200_multi_canvas", "gudni_b200_multi_frame", "gudni_b200_partition_rows", "gudni_b200_rebalance_rows",
 ]
 
 
@@ -56,6 +59,8 @@ def load_library():
     L.gudni_b200_init.argtypes = [i32, c.POINTER(CSpec), c.POINTER(CSpec), c.POINTER(vp)]
     L.gudni_b200_frame_begin.argtypes = [vp, vp, sz, vp, i32, vp, sz, vp, i32, vp, i32, i32, i32]
     L.gudni_b200_frame_begin_device.argtypes = [vp, vp, sz, vp, i32, vp, sz, vp, i32, vp, i32, i32, i32]
+    L.gudni_b200_frame_begin_cached.argtypes = [vp, vp, sz, vp, i32, vp, sz, vp, i32, vp, i32, i32, i32, vp]
+    L.gudni_b200_raster_scene_cached.argtypes = [vp, vp, i32, c.c_uint64]
     L.gudni_b200_frame_strip.argtypes = [vp, i32, i32]
     L.gudni_b200_raster_job.argtypes = [vp, vp, i32, vp, i32, i32, i32]
     L.gudni_b200_raster_scene.argtypes = [vp, vp, i32]
@@ -176,16 +181,19 @@ class Rasterizer:
             pass
 
     # -- the reference's call sequence -----------------------------------------------------------
-    def frame_begin(self, scene, frame_count=0):
+    def frame_begin(self, scene, frame_count=0, generations=None):
+        """`generations`: None, or (geometry, substances, pictures, picture_uses, entries) counters for the input
+        cache (gudni_b200_frame_begin_cached): an input whose counter is nonzero and unchanged is not uploaded again."""
         g = np.ascontiguousarray(scene.geometry)
         s = np.ascontiguousarray(scene.substances, np.float32)
         p = np.ascontiguousarray(scene.picture_bytes)
         u = np.ascontiguousarray(scene.picture_uses)
         bg = np.ascontiguousarray(scene.background, np.float32)
         self._keep = (g, s, p, u, bg)
-        self._check(self._L.gudni_b200_frame_begin(self._ctx, _ptr(g), g.nbytes, _ptr(s), len(s), _ptr(p), p.nbytes,
-                                                   _ptr(u), len(u), bg.ctypes.data, scene.width, scene.height,
-                                                   frame_count))
+        gen = (ctypes.c_uint64 * 5)(*generations) if generations is not None else None
+        self._check(self._L.gudni_b200_frame_begin_cached(self._ctx, _ptr(g), g.nbytes, _ptr(s), len(s), _ptr(p), p.nbytes,
+                                                          _ptr(u), len(u), bg.ctypes.data, scene.width, scene.height,
+                                                          frame_count, gen))
         self._dims = (scene.height, scene.width)
         self._rows = (0, scene.height)
 
@@ -210,9 +218,9 @@ class Rasterizer:
         self._check(self._L.gudni_b200_raster_job(self._ctx, _ptr(shapes), len(shapes), _ptr(tiles), len(tiles),
                                                   job.columns, job_index))
 
-    def raster_entries(self, entries):
+    def raster_entries(self, entries, generation=0):
         e = np.ascontiguousarray(entries)
-        self._check(self._L.gudni_b200_raster_scene(self._ctx, _ptr(e), len(e)))
+        self._check(self._L.gudni_b200_raster_scene_cached(self._ctx, _ptr(e), len(e), generation))
 
     def raster_entries_device(self, dev_entries, n):
         self._check(self._L.gudni_b200_raster_scene_device(self._ctx, dev_entries, n))
@@ -233,14 +241,14 @@ class Rasterizer:
             self.raster_job(job, index)
         return self.frame_end(out)
 
-    def raster_scene(self, frame_count, scene, out=None, rows=None):
+    def raster_scene(self, frame_count, scene, out=None, rows=None, generations=None):
         """buildRasterJobs + queueRasterJobs with the tile binning done on the GPU (level 2)."""
-        self.frame_begin(scene, frame_count)
+        self.frame_begin(scene, frame_count, generations)
         entries = scene.entries
         if rows is not None:
             self.frame_strip(*rows)
             entries = scene.subset_rows(*rows)
-        self.raster_entries(entries)
+        self.raster_entries(entries, generations[4] if generations is not None else 0)
         return self.frame_end(out)
 
     def frame_begin_outlines(self, scene, frame_count=0):

@@ -157,6 +157,27 @@ int gudni_b200_frame_begin(gudni_ctx* ctx,
                            const float background_rgba[4],
                            int width, int height, int frame_number);
 
+/* Persistent input cache.  The reference packs and uploads pictures, geometry and
+ * substances again every frame (OpenCL/CallKernels.hs:229-235), changed or not.  The caller knows when a Pile
+ * changed; it says so with a generation counter per input: a buffer is uploaded unless its generation is nonzero
+ * and equal to the generation, pointer-independent, under which the same number of bytes was last uploaded into
+ * this context.  Counters, not content hashes: hashing 30 MB on the host costs more than sending it, and a
+ * pointer comparison would be wrong for Piles that are refilled in place — the caller bumps the counter when it
+ * refills.  generation 0 = always upload (what gudni_b200_frame_begin does).  `entries` covers the shape-entry
+ * array of gudni_b200_raster_scene_cached. */
+typedef struct gudni_generations {
+    uint64_t geometry, substances, pictures, picture_uses, entries;
+} gudni_generations;
+int gudni_b200_frame_begin_cached(gudni_ctx* ctx,
+                                  const void* geometry, size_t geometry_bytes,
+                                  const float* substances, int n_substances,
+                                  const uint8_t* picture_bytes, size_t n_picture_bytes,
+                                  const gudni_picture_use* picture_uses, int n_picture_uses,
+                                  const float background_rgba[4],
+                                  int width, int height, int frame_number,
+                                  const gudni_generations* generations);
+int gudni_b200_raster_scene_cached(gudni_ctx* ctx, const gudni_shape_entry* entries, int n_entries, uint64_t generation);
+
 /* Restrict this context to canvas rows [row_begin, row_end) (whole rows of root tiles).  Used by
  * the multi-GPU strip partition (no reference counterpart: one OpenCLState = one device,
  * OpenCL/Setup.hs:118-120).  row_begin = 0, row_end = height restores the full frame. Must be
@@ -186,6 +207,49 @@ int gudni_b200_raster_scene(gudni_ctx* ctx, const gudni_shape_entry* entries, in
  * hang), so the raster kernels were not let near it.  NaN and large finite coordinates render as in the
  * reference.  The context stays usable. */
 int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats);
+
+/* ---- several GPUs of one box, one process ------------------------------------------------------
+ * No reference counterpart: one OpenCLState is one device (OpenCL/Setup.hs:118-120) and queueRasterJobs
+ * (OpenCL/CallKernels.hs:218-242) hands it every job.  gudni_b200_multi_frame is queueRasterJobs for a canvas that
+ * is worth sharding (a 16K x 16K canvas; a frame that fits one GPU is better left on one): the canvas is cut into
+ * strips of whole root-tile rows, one per device, re-cut every frame from the devices' measured times; each device
+ * bins and rasterizes the shapes that touch its strip (its own context, its own host thread) and copies its rows
+ * straight into `out_bgra` over its own PCIe link.  With a presenting device set (gudni_b200_multi_set_presenting)
+ * the strips are also pushed over NVLink into one canvas on that device (gudni_b200_multi_canvas), for a presenter
+ * that keeps the frame on the GPU.  `devices` may be NULL (0 .. n_devices-1) and may name a device twice (two
+ * contexts on one GPU: how the path is tested on a one-GPU box). */
+#define GUDNI_MULTI_MAX_DEVICES 16
+typedef struct gudni_multi gudni_multi;
+typedef struct gudni_multi_stats {
+    int32_t n_devices;
+    int32_t device[GUDNI_MULTI_MAX_DEVICES];
+    int32_t row_begin[GUDNI_MULTI_MAX_DEVICES], row_end[GUDNI_MULTI_MAX_DEVICES];   /* this frame's strips */
+    float   ms_device[GUDNI_MULTI_MAX_DEVICES];   /* strands + binning + raster kernels of the strip (CUDA events) */
+    float   ms_frame;                             /* wall clock of the call                                         */
+    float   ms_gather_exposed;                    /* last strip landed - last device done rasterizing               */
+    gudni_stats total;                            /* counts summed over the devices, stage times the maximum        */
+} gudni_multi_stats;
+int gudni_b200_multi_init(int n_devices, const int* devices, const gudni_spec* want, gudni_spec* got, gudni_multi** out);
+void gudni_b200_multi_destroy(gudni_multi* m);
+const char* gudni_b200_multi_last_error(gudni_multi* m);
+/* device_index: index into the devices given to multi_init, or -1 for no device-side canvas (the default) */
+int gudni_b200_multi_set_presenting(gudni_multi* m, int device_index);
+int gudni_b200_multi_canvas(gudni_multi* m, void** dev_bgra, int* device);
+/* frame_begin_cached + raster_scene_cached + frame_end for the whole canvas.  out_bgra: width*height words, may be NULL. */
+int gudni_b200_multi_frame(gudni_multi* m,
+                           const void* geometry, size_t geometry_bytes,
+                           const float* substances, int n_substances,
+                           const uint8_t* picture_bytes, size_t n_picture_bytes,
+                           const gudni_picture_use* picture_uses, int n_picture_uses,
+                           const float background_rgba[4], int width, int height, int frame_number,
+                           const gudni_shape_entry* entries, int n_entries,
+                           const gudni_generations* generations,
+                           uint32_t* out_bgra, gudni_multi_stats* stats);
+/* The strip partition by itself (host arithmetic, no GPU needed): first cut from the shapes' boxes, and the feedback
+ * cut from last frame's strips and per-device times.  rows: n_devices pairs (row_begin, row_end). */
+int gudni_b200_partition_rows(const gudni_shape_entry* entries, int n_entries, int width, int height, int tile_rows, int n_devices,
+                              int* rows_out);
+int gudni_b200_rebalance_rows(const int* rows_in, const double* ms, int n_devices, int height, int tile_rows, int* rows_out);
 
 /* Device-side access for callers that keep data on the GPU (bench, multi-GPU gather).  The frame
  * pointer stays valid until the next frame_begin with a different size, or destroy. */

@@ -101,3 +101,26 @@ def test_records_that_leave_the_geometry_heap_are_refused(rasterizer):
         rasterizer.raster_scene(0, bad2)
     img, stats = rasterizer.raster_scene(1, scene)
     assert np.array_equal(img, good.image)
+
+
+def test_input_cache_skips_unchanged_uploads(rasterizer):
+    """gudni_b200_frame_begin_cached: with unchanged generation counters the second frame uploads nothing and is the
+    same image; a bumped counter picks up a buffer refilled in place; generation 0 always uploads."""
+    import numpy as np
+    from gudni_b200 import scenes
+    scene = scenes.fuzzy_circles(20000, 1920, 1080, 5, 50, 0xCAC4E)
+    gens = [7, 7, 7, 7, 7]
+    first, st1 = rasterizer.raster_scene(0, scene, generations=gens)
+    again, st2 = rasterizer.raster_scene(1, scene, generations=gens)
+    assert np.array_equal(first, again)
+    assert st2.ms_upload < 0.25 * st1.ms_upload + 0.02, (st1.ms_upload, st2.ms_upload)
+    # refill the substances in place: without a new counter the library may keep what it has ...
+    scene.substances = np.ascontiguousarray(scene.substances, np.float32).copy()
+    scene.substances[:, :3] = scene.substances[:, :3][:, ::-1]
+    stale, _ = rasterizer.raster_scene(2, scene, generations=gens)
+    assert np.array_equal(stale, first)
+    # ... with one it does not
+    gens[1] = 8
+    fresh, _ = rasterizer.raster_scene(3, scene, generations=gens)
+    plain, _ = rasterizer.raster_scene(4, scene)
+    assert np.array_equal(fresh, plain) and not np.array_equal(fresh, first)
