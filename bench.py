@@ -308,9 +308,9 @@ def run_native(args, rank, world, local_rank):
     r = setup_rasterizer(local_rank)
     stream = torch.cuda.current_stream()
     r.set_stream(stream.cuda_stream)
-    strips = StripRenderer(r, scene, rank, world, dist, mode=args.gather)
+    strips = StripRenderer(r, scene, rank, world, dist, mode="p2p" if args.gather == "p2p" else "nccl")
     dscene = DeviceScene(r, scene, entries=strips.entries)
-    pipelined = world > 1 and args.gather == "nccl" and args.pipeline
+    pipelined = world > 1 and args.gather in ("nccl", "auto") and args.pipeline
     if pipelined:
         strips.prepare_chunks(dscene.put_entries, chunk_rows=args.chunk_rows)
     render = (lambda f: strips.render_pipelined(f, dscene)) if pipelined else (lambda f: strips.render(f, dscene))
@@ -324,6 +324,7 @@ def run_native(args, rank, world, local_rank):
 
     # ---- value: inputs resident in HBM, frame left in HBM -----------------------------------------
     single = None
+    solo_canvas = None
     if world > 1:
         # the same workload on ONE GPU, measured by rank 0 in this run, so the strong-scaling ratio
         # can be read off this line alone (bench.py --gpus 1 measures the 4K scene, not this one)
@@ -340,20 +341,25 @@ def run_native(args, rank, world, local_rank):
                 torch.cuda.synchronize()
                 t.append(e0.elapsed_time(e1))
             single = {"ms_per_step": float(np.mean(t)), "value": 1e3 / float(np.mean(t)), "unit": "frames/s"}
+            solo_canvas = solo.canvas.clone()      # the whole frame from ONE GPU: what the gathered canvas must equal
             solo.close(); dsolo.free(); del solo
         barrier()
     for i in range(args.warmup):
         render(i)
     gather_order = None
-    if world > 1 and args.gather == "nccl" and not args.no_rebalance:
+    if world > 1 and not pipelined and not args.no_rebalance:
         # Feedback partition (contiguous tile-row strips stay): a few rounds of "measure every rank's strip, cut
-        # the canvas again", under each of the two gather orders, keeping the faster one:
-        #   early  the presenting rank posts its receives before its own strip; strips queue on its inbound
-        #          links in the order their ranks finish, so each strip is charged the transfer of everything
-        #          from its first row down (ranks finish staggered); the receive kernel holds some SMs meanwhile
-        #   late   receives after the presenting rank's strip: nothing arrives before it is done, so it is charged
-        #          the transfer of all the other strips too
+        # the canvas again" under each way of getting the strips to the presenting rank, keeping the fastest:
+        #   nccl/early  the presenting rank posts its receives before its own strip; strips queue on its inbound
+        #               links in the order their ranks finish, so each strip is charged the transfer of everything
+        #               from its first row down (ranks finish staggered); the receive kernel holds some SMs meanwhile
+        #   nccl/late   receives after the presenting rank's strip: nothing arrives before it is done, so it is charged
+        #               the transfer of all the other strips too
+        #   p2p         the presenting rank's canvas is mapped into every process (CUDA IPC) and the accumulate kernel
+        #               stores its finished 128-byte rows there directly over NVLink: the transfer rides along with
+        #               the rasterization, a barrier closes the frame; strips are balanced on kernel time alone
         from gudni_b200.strips import rebalance_rows
+        from gudni_b200 import multi as multi_abi
         row_ms = 4.0 * scene.width * r.spec.max_tile_size / args.gather_gbs / 1e9 * 1e3
         start_rows = list(strips.rows)
 
@@ -369,38 +375,52 @@ def run_native(args, rank, world, local_rank):
             dist.all_reduce(m, op=dist.ReduceOp.MAX)
             return float(m.item())
 
-        def rebuild(rows, early):
+        def rebuild(rows, mode, early):
             nonlocal strips, dscene, render
             strips.close(); dscene.free()
-            strips = StripRenderer(r, scene, rank, world, dist, mode=args.gather, rows=rows, early_receives=early)
+            strips = StripRenderer(r, scene, rank, world, dist, mode=mode, rows=rows, early_receives=early)
             dscene = DeviceScene(r, scene, entries=strips.entries)
             render = lambda f: strips.render(f, dscene)
             for i in range(2):
                 render(i)
 
+        if args.gather == "auto":
+            candidates = [("nccl", "early"), ("nccl", "late"), ("p2p", None)]
+        elif args.gather == "p2p":
+            candidates = [("p2p", None)]
+        else:
+            candidates = [("nccl", o) for o in (["early", "late"] if args.gather_order == "auto" else [args.gather_order])]
         tried = {}
-        orders = ["early", "late"] if args.gather_order == "auto" else [args.gather_order]
-        for order in orders:
-            rebuild(start_rows, order == "early")
+        for mode, order in candidates:
+            rebuild(start_rows, mode, order == "early")
             for it in range(args.rebalance_rounds):
                 st = getattr(strips, "last_stats", None)
                 mine = torch.tensor([st.ms_raster + st.ms_bin if st is not None else 0.0], dtype=torch.float64, device="cuda")
                 allr = [torch.zeros_like(mine) for _ in range(world)]
                 dist.all_gather(allr, mine)
                 times = [float(x.item()) for x in allr]
-                if order == "early":
-                    new_rows = rebalance_rows(strips.rows, times, scene.height, r.spec.max_tile_size, 0, 0.0, row_ms)
+                if mode == "p2p":     # kernel time alone: the C ABI's own rebalancer (gudni_b200_rebalance_rows)
+                    new_rows = multi_abi.rebalance_rows(strips.rows, times, scene.height, r.spec.max_tile_size)
                 else:
                     new_rows = rebalance_rows(strips.rows, times, scene.height, r.spec.max_tile_size, 0, 0.0, row_ms,
-                                              late_receives=True)
+                                              late_receives=(order == "late"))
                 if new_rows == strips.rows:
                     break
-                rebuild(new_rows, order == "early")
-            tried[order] = (frame_ms(), list(strips.rows))
-        gather_order = min(tried, key=lambda k: tried[k][0])
-        if len(tried) > 1 or strips.rows != tried[gather_order][1]:
-            rebuild(tried[gather_order][1], gather_order == "early")
-        gather_order = {"order": gather_order, "warmup_ms": {k: round(v[0], 3) for k, v in tried.items()}}
+                rebuild(new_rows, mode, order == "early")
+            tried[(mode, order)] = (frame_ms(), list(strips.rows))
+        best = min(tried, key=lambda k: tried[k][0])
+        if len(tried) > 1 or strips.rows != tried[best][1]:
+            rebuild(tried[best][1], best[0], best[1] == "early")
+        gather_order = {"gather": best[0], "order": best[1],
+                        "warmup_ms": {f"{k[0]}/{k[1]}" if k[1] else k[0]: round(v[0], 3) for k, v in tried.items()}}
+    parity_ok = None
+    if world > 1:
+        # pixel evidence for the scaling record: the canvas gathered from N GPUs against the single-GPU frame
+        canvas = render(args.warmup)
+        barrier()
+        if rank == 0:
+            parity_ok = bool(torch.equal(canvas, solo_canvas))
+            del solo_canvas
     launches0 = r.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -437,37 +457,29 @@ def run_native(args, rank, world, local_rank):
     e2e_times = []
     h2d = (scene.geometry.nbytes + scene.substances.nbytes + scene.picture_bytes.nbytes + scene.picture_uses.nbytes +
            strips.entries.nbytes)
-    rows = strips.my_rows[1] - strips.my_rows[0]
-    d2h = 4 * scene.width * (scene.height if world == 1 else 0)
-    host_img = np.empty((scene.height, scene.width), dtype=np.uint32) if (rank == 0 and world == 1) else None
-    pinned_canvas = torch.empty((scene.height, scene.width), dtype=torch.int32, pin_memory=True) if (rank == 0 and world > 1) else None
-    # the base contract's e2e leg copies from / to pinned host memory: page-lock the caller-side buffers
-    # once (gudni_b200_host_register), as a client with long-lived Piles would
-    pinned = [a for a in (scene.geometry, scene.substances, scene.entries, scene.picture_bytes, host_img)
-              if a is not None and a.nbytes and world == 1]
-    for a in pinned:
-        r.host_register(a)
+    d2h = 4 * scene.width * scene.height
+    e2e_pageable = None
+    e2e_note = None
     n_e2e = max(3, min(args.steps, 10))
-    for i in range(2 + n_e2e):
-        barrier()
-        t0 = time.perf_counter()
-        if world == 1:
+    if world == 1:
+        host_img = np.empty((scene.height, scene.width), dtype=np.uint32)
+        # the base contract's e2e leg copies from / to pinned host memory: page-lock the caller-side buffers
+        # once (gudni_b200_host_register), as a client with long-lived Piles would
+        pinned = [a for a in (scene.geometry, scene.substances, scene.entries, scene.picture_bytes, host_img)
+                  if a is not None and a.nbytes]
+        for a in pinned:
+            r.host_register(a)
+        for i in range(2 + n_e2e):
+            barrier()
+            t0 = time.perf_counter()
             r.frame_target(None)
             r.raster_scene(i, scene, out=host_img)
-        else:
-            canvas = strips.render(i, None)
-            if rank == 0:
-                pinned_canvas.copy_(canvas, non_blocking=True)
-                torch.cuda.synchronize()
-                d2h = 4 * scene.width * scene.height
-        barrier()
-        if i >= 2:
-            e2e_times.append(time.perf_counter() - t0)
-    for a in pinned:
-        r.host_unregister(a)
-    # the same call with the caller's buffers left pageable (what an unmodified Haskell caller has: SURVEY.md §8(b))
-    e2e_pageable = None
-    if world == 1:
+            barrier()
+            if i >= 2:
+                e2e_times.append(time.perf_counter() - t0)
+        for a in pinned:
+            r.host_unregister(a)
+        # the same call with the caller's buffers left pageable (what an unmodified Haskell caller has: SURVEY.md §8(b))
         tp = []
         for i in range(2 + n_e2e):
             t0 = time.perf_counter()
@@ -476,6 +488,58 @@ def run_native(args, rank, world, local_rank):
                 tp.append(time.perf_counter() - t0)
         e2e_pageable = {"value": 1.0 / float(np.mean(tp)), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "buffers": "pageable host memory (no cudaHostRegister)"}
+    else:
+        # A host presenter needs no inter-GPU gather at all: every rank rasterizes its strip from host buffers and
+        # copies it over ITS OWN PCIe link into its rows of one canvas in POSIX shared memory that every rank has
+        # page-locked; the closing barrier is the hand-over to the presenting process.
+        from multiprocessing import shared_memory
+        name = f"gudni_b200_canvas_{os.environ.get('MASTER_PORT', '0')}"
+        shm = None
+        if rank == 0:
+            try:
+                shared_memory.SharedMemory(name=name).unlink()
+            except FileNotFoundError:
+                pass
+            shm = shared_memory.SharedMemory(name=name, create=True, size=d2h)
+        barrier()
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name)
+            try:   # rank 0 owns the segment: keep this process's resource tracker from unlinking it again at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:  # noqa: BLE001
+                pass
+        host_canvas = np.ndarray((scene.height, scene.width), dtype=np.uint32, buffer=shm.buf)
+        mine = host_canvas[strips.my_rows[0]:strips.my_rows[1]]
+        h2d_all = torch.tensor([float(h2d)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(h2d_all)
+        h2d = int(h2d_all.item())
+        pinned = [a for a in (scene.geometry, scene.substances, strips.entries, scene.picture_bytes, mine) if a is not None and a.nbytes]
+        for a in pinned:
+            r.host_register(a)
+        for i in range(2 + n_e2e):
+            barrier()
+            t0 = time.perf_counter()
+            strips.render_to_host(i, host_canvas)
+            barrier()
+            if i >= 2:
+                e2e_times.append(time.perf_counter() - t0)
+        for a in pinned:
+            r.host_unregister(a)
+        e2e_note = ("every rank uploads its inputs and copies its strip over its own PCIe link into one page-locked canvas "
+                    "in POSIX shared memory; no NVLink gather for a host presenter")
+        if rank == 0:
+            e2e_parity = None
+            try:
+                e2e_parity = bool(np.array_equal(host_canvas, strips.canvas.cpu().numpy().view(np.uint32))) if strips.canvas is not None else None
+            except Exception:  # noqa: BLE001
+                pass
+            e2e_note += f"; canvas equals the device-gathered frame: {e2e_parity}"
+        del mine, host_canvas
+        barrier()
+        shm.close()
+        if rank == 0:
+            shm.unlink()
     t_e2e = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -500,7 +564,7 @@ def run_native(args, rank, world, local_rank):
                        "spec": "G=256 MAXT=1024 maxStrandsPerTile=1022 MAXSHAPE=127",
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": "1 GPU, whole frame" if world == 1 else
-                       f"{world} tile-row strips, gather={args.gather}" + (f", pipelined in chunks of {args.chunk_rows} rows" if pipelined else ""),
+                       f"{world} tile-row strips, gather={(gather_order or {}).get('gather', args.gather)}" + (f", pipelined in chunks of {args.chunk_rows} rows" if pipelined else ""),
                        "strips": strips.rows if world > 1 else None,
                        "gather_order": gather_order},
             "mpixel_per_s": scene.width * scene.height * value / 1e6,
@@ -509,7 +573,7 @@ def run_native(args, rank, world, local_rank):
             "staged_bytes": int(a_bytes + 2 * 20 * stats.n_thresholds) if (stats is not None and world == 1) else None,
             "clocks": clocks,
             "e2e": {"value": 1.0 / float(t_e2e.item()), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
+                    "d2h_bytes_per_step": int(d2h), **({"note": e2e_note} if e2e_note else {})},
             "e2e_pageable": e2e_pageable,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -525,6 +589,10 @@ def run_native(args, rank, world, local_rank):
         }
         if per_rank is not None:
             line["per_rank_raster_bin_ms"] = per_rank
+            slowest = max(a + b for a, b in per_rank)
+            line["exposed_gather_ms"] = max(0.0, ms_per_step - slowest)   # frame minus the slowest rank's kernels: gather + launch/host gaps
+            line["parity_ok"] = parity_ok
+            line["parity_note"] = "torch.equal(canvas gathered from N GPUs, the same frame rendered on one GPU), checked on rank 0 before the timed steps"
         if single is not None:
             line["single_gpu_same_workload"] = single
             line["speedup_vs_single_gpu"] = value / single["value"]
@@ -601,7 +669,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="N > 1: how strips reach the presenting rank: NCCL send/recv, direct stores over NVLink into its "
+                         "CUDA-IPC-mapped canvas, or (auto) whichever the warm-up frames show to be faster")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary S4b reading")
     ap.add_argument("--no-opencl-reference", action="store_true",

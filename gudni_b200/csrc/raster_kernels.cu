@@ -14,6 +14,10 @@ using namespace gudni_dev;
 #ifndef GUDNI_COLOR_WARPS
 #define GUDNI_COLOR_WARPS 4
 #endif
+#ifndef GUDNI_MAX_LANE_SHIFT
+#define GUDNI_MAX_LANE_SHIFT 0       // whole-warp units.  Narrower ones measured slower on a 2,048-row strip of S5 (3.81 ms with
+#endif                               // 32 lanes, 3.96 with 16, 4.87 with 8): a unit's time is the latency of its longest column's
+                                     // chain of records, not the number of lanes that diverge, so narrower units only add waves
 constexpr int kSliceWarpsPerCta = GUDNI_SLICE_WARPS;
 constexpr int kColorWarpsPerCta = GUDNI_COLOR_WARPS;
 
@@ -105,9 +109,38 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
 #ifndef GUDNI_SLICE_MIN_CTAS
 #define GUDNI_SLICE_MIN_CTAS 8      // 64 registers: 32 warps per SM hide the divergent kernel's latencies (96 registers / 20 warps: +1.1 ms on S4)
 #endif
+// Persistent-warp loop over the units of a launch, most expensive tiles first.  A unit is 32 >> laneShift
+// neighbouring column-threads of a tile (the reference's work-group sliced by warps, `Work2D numTiles
+// threadsPerTile`, OpenCL/CallKernels.hs:141-142).  laneShift > 0 (narrower units for launches with few tiles) is
+// kept as a build option; it measured slower, see GUDNI_MAX_LANE_SHIFT.
+// body(tileIndex, tile, rec, column) is called by the whole warp for every unit of a dense tile; rec is the
+// lane's thread record, or null for a lane beyond the unit's width.
+template <class F>
+__device__ __forceinline__ void forEachUnit(const FrameParams& P, int tileBase, int nTiles, int counterSlot, F body) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int unitShift = P.computeDepth - 5 + P.laneShift;            // units per tile
+    const int lanesPerUnit = 32 >> P.laneShift;
+    const unsigned totalUnits = (unsigned)nTiles << unitShift;
+    const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
+    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + counterSlot);
+    for (;;) {
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd(workCounter, 1u);
+        unit = __shfl_sync(full, unit, 0);
+        if (unit >= totalUnits) break;
+        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> unitShift)];
+        const unsigned unitInTile = unit & ((1u << unitShift) - 1u);
+        const gudni_tile tile = P.tiles[tileIndex];
+        if (tile.shape_count > denseCap) continue;   // replayed lane-privately
+        const int column = (int)(unitInTile * (unsigned)lanesPerUnit) + min(lane, lanesPerUnit - 1);
+        ThreadRec* rec = lane < lanesPerUnit ? P.threadRecs + (((size_t)tileIndex << P.computeDepth) + (size_t)column) : nullptr;
+        body(tileIndex, tile, rec, column);
+    }
+}
+
 __global__ void __launch_bounds__(kSliceWarpsPerCta * 32, GUDNI_SLICE_MIN_CTAS) raster_slice_kernel(const FrameParams P, int tileBase, int nTiles) {
     __shared__ SliceScratch scratch[kSliceWarpsPerCta];
-    const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     SliceScratch& W = scratch[warp];
     if (lane == 0) { W.slabNext = 0u; W.slabEnd = 0u; }
@@ -116,54 +149,17 @@ __global__ void __launch_bounds__(kSliceWarpsPerCta * 32, GUDNI_SLICE_MIN_CTAS) 
     q.limit = min(kQueueCap, P.maxThresholds);
     q.thrHot = W.qThr + lane;
     q.hdrHot = W.qHdr + lane;
-    const int warpShift = P.computeDepth - 5;
-    const unsigned totalUnits = (unsigned)nTiles << warpShift;
-    const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
-    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkSweep);
-    for (;;) {
-        unsigned unit = 0;
-        if (lane == 0) unit = atomicAdd(workCounter, 1u);
-        unit = __shfl_sync(full, unit, 0);
-        if (unit >= totalUnits) break;
-        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> warpShift)];
-        const unsigned warpInTile = unit & ((1u << warpShift) - 1u);
-        const int column = (int)(warpInTile << 5) + lane;
-        const unsigned recUnit = ((unsigned)tileIndex << warpShift) + warpInTile;
-        const gudni_tile tile = P.tiles[tileIndex];
-        if (tile.shape_count > denseCap) continue;   // replayed lane-privately
-        const unsigned int count = P.threadRecs[(size_t)recUnit * 32 + lane].count;
+    forEachUnit(P, tileBase, nTiles, kCntWorkSweep, [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
+        const unsigned int count = rec ? rec->count : 0u;
         bool exhausted = false;
-        const int failed = sliceWarp(P, W, q, tile, recUnit, column, exhausted);
+        const int failed = sliceWarp(P, W, q, tile, rec, column, exhausted);
         if (failed) {
             // its thresholds were counted by the generate kernel; the replay counts them again
             atomicAdd(&P.counters[kCntThresholds], 0ull - (unsigned long long)count);
             if (exhausted) atomicAdd(&P.counters[kCntExhausted], 1ull);
             registerSpill(P, tileIndex, column);
         }
-    }
-}
-
-// Persistent-warp loop over the (tile, 32-column group) units of a launch, most expensive tiles first.
-// body(tileIndex, tile, recUnit, column) is called by the whole warp for every unit of a dense tile.
-template <class F>
-__device__ __forceinline__ void forEachUnit(const FrameParams& P, int tileBase, int nTiles, int counterSlot, F body) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int warpShift = P.computeDepth - 5;
-    const unsigned totalUnits = (unsigned)nTiles << warpShift;
-    const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
-    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + counterSlot);
-    for (;;) {
-        unsigned unit = 0;
-        if (lane == 0) unit = atomicAdd(workCounter, 1u);
-        unit = __shfl_sync(full, unit, 0);
-        if (unit >= totalUnits) break;
-        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> warpShift)];
-        const unsigned warpInTile = unit & ((1u << warpShift) - 1u);
-        const gudni_tile tile = P.tiles[tileIndex];
-        if (tile.shape_count > denseCap) continue;   // replayed lane-privately
-        body(tileIndex, tile, ((unsigned)tileIndex << warpShift) + warpInTile, (int)(warpInTile << 5) + lane);
-    }
+    });
 }
 
 #ifndef GUDNI_RESOLVE_WARPS
@@ -184,10 +180,10 @@ __global__ void __launch_bounds__(kResolveWarpsPerCta * 32) raster_resolve_kerne
     __shared__ ResolveScratch scratch[kResolveWarpsPerCta];
     ResolveScratch& W = scratch[threadIdx.x >> 5];
     RefSlab slab{kRefNone, 0u, -1};
-    forEachUnit(P, tileBase, nTiles, kCntWorkResolve, [&](int tileIndex, const gudni_tile& tile, unsigned recUnit, int column) {
+    forEachUnit(P, tileBase, nTiles, kCntWorkResolve, [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
         if (tileHasPictures(P, tile)) return;   // raster_picture_kernel
-        const unsigned int count = P.threadRecs[(size_t)recUnit * 32 + (threadIdx.x & 31)].count;
-        if (resolveWarp(P, W, slab, tileIndex, recUnit)) {
+        const unsigned int count = rec ? rec->count : 0u;
+        if (resolveWarp(P, W, slab, tileIndex, rec)) {
             atomicAdd(&P.counters[kCntThresholds], 0ull - (unsigned long long)count);
             atomicAdd(&P.counters[kCntExhausted], 1ull);
             registerSpill(P, tileIndex, column);
@@ -220,9 +216,9 @@ __global__ void __launch_bounds__(kCompositeWarpsPerCta * 32) raster_composite_k
 __global__ void __launch_bounds__(kAccumulateWarpsPerCta * 32) raster_accumulate_kernel(const FrameParams P, int tileBase, int nTiles) {
     __shared__ AccumScratch scratch[kAccumulateWarpsPerCta];
     AccumScratch& W = scratch[threadIdx.x >> 5];
-    forEachUnit(P, tileBase, nTiles, kCntWorkAccumulate, [&](int, const gudni_tile& tile, unsigned recUnit, int column) {
+    forEachUnit(P, tileBase, nTiles, kCntWorkAccumulate, [&](int, const gudni_tile& tile, ThreadRec* rec, int column) {
         if (tileHasPictures(P, tile)) return;
-        accumulateWarp(P, W, tile, recUnit, column);
+        accumulateWarp(P, W, tile, rec, column);
         __syncwarp();
     });
 }
@@ -231,12 +227,12 @@ __global__ void __launch_bounds__(kAccumulateWarpsPerCta * 32) raster_accumulate
 __global__ void __launch_bounds__(kColorWarpsPerCta * 32) raster_picture_kernel(const FrameParams P, int tileBase, int nTiles) {
     __shared__ TileTable tables[kColorWarpsPerCta];
     TileTable& T = tables[threadIdx.x >> 5];
-    forEachUnit(P, tileBase, nTiles, kCntWorkColor, [&](int, const gudni_tile& tile, unsigned recUnit, int column) {
+    forEachUnit(P, tileBase, nTiles, kCntWorkColor, [&](int, const gudni_tile& tile, ThreadRec* rec, int column) {
         __syncwarp();
         bool anyPicture, anyWild;
         buildTileTable(P, T, tile, anyPicture, anyWild);
         __syncwarp();
-        if (anyPicture) pictureWarp(P, T, tile, recUnit, column);
+        if (anyPicture) pictureWarp(P, T, tile, rec, column);
     });
 }
 
@@ -415,7 +411,10 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkGenerate, 0, 8, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkColor, 0, 8, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkResolve, 0, 24, ctx->stream));
-    const long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
+    // units narrower than a warp when whole-warp units would not go round (see forEachUnit)
+    long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
+    P.laneShift = 0;
+    while (P.laneShift < GUDNI_MAX_LANE_SHIFT && units < 4ll * numSms * ctx->sliceCtasPerSm * kSliceWarpsPerCta) { P.laneShift++; units *= 2; }
     auto grid = [&](int ctasPerSm, int warpsPerCta) {
         return (int)std::min<long long>((long long)ctasPerSm * numSms, (units + warpsPerCta - 1) / warpsPerCta);
     };

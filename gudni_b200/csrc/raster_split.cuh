@@ -156,8 +156,9 @@ __device__ __forceinline__ void sliceVertical(const FrameParams& P, SliceScratch
 // ---- slice kernel body -------------------------------------------------------------------------------------------
 // One warp, one (tile, 32-column group) of a dense tile.  Returns per lane 1 if the thread has to be replayed
 // (its queue outgrew the on-chip capacity while slicing, or the stream pool ran out: `exhausted`).
+// `rec`: the lane's thread record, null for a lane that has no column-thread in this unit (units narrower than a warp)
 __device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, LaneQueue& q, const gudni_tile& tile,
-                                         unsigned unit, int column, bool& exhausted) {
+                                         ThreadRec* recp, int column, bool& exhausted) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const ThreadGeom g = threadGeom(P, tile, column);
@@ -166,8 +167,7 @@ __device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, 
     for (uint32_t i = lane; i < tile.shape_count; i += 32)
         anyPicture = anyPicture || (tagMeta(__ldg(&P.shapes[tile.shape_start + i].tag)) & kMetaPicture);
     const bool foldable = !__any_sync(full, anyPicture);
-    ThreadRec* recp = P.threadRecs + (size_t)unit * 32 + lane;
-    const unsigned int recOffset = recp->offset, recCount = recp->count;
+    const unsigned int recOffset = recp ? recp->offset : 0u, recCount = recp ? recp->count : kRecInactive;
     const bool mine = recCount != kRecInactive;
     const float floatHeight = (float)g.intHeight;
     SweepState st;
@@ -327,7 +327,7 @@ __device__ __forceinline__ void closeSlab(const FrameParams& P, RefSlab& slab) {
 
 // One warp, one (tile, 32-column group) of a dense tile without pictures.  Returns per lane 1 if the stack table
 // ran out under this thread (it is handed to the replay).
-__device__ __forceinline__ int resolveWarp(const FrameParams& P, ResolveScratch& W, RefSlab& slab, int tileIndex, unsigned unit) {
+__device__ __forceinline__ int resolveWarp(const FrameParams& P, ResolveScratch& W, RefSlab& slab, int tileIndex, ThreadRec* recp) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     if (slab.tileIndex != tileIndex) {   // numbers are only shared inside a tile: new slab, empty cache
@@ -335,8 +335,9 @@ __device__ __forceinline__ int resolveWarp(const FrameParams& P, ResolveScratch&
         slab.tileIndex = tileIndex;
         for (int i = lane; i < kColorLines; i += 32) W.ref[i] = kRefNone;
     }
-    ThreadRec* recp = P.threadRecs + (size_t)unit * 32 + lane;
-    const ThreadRec rec = *recp;
+    ThreadRec rec{};
+    rec.count = kRecInactive;
+    if (recp) rec = *recp;
     ShapeStack base{rec.lo, rec.hi}, cur{rec.lo, rec.hi};
     bool done = rec.count == kRecInactive;
     bool failed = false;
@@ -420,7 +421,7 @@ __device__ __forceinline__ int resolveWarp(const FrameParams& P, ResolveScratch&
             }
         }
     }
-    if (failed) recp->count = kRecInactive;
+    if (failed && recp) recp->count = kRecInactive;
     return failed ? 1 : 0;
 }
 
@@ -544,11 +545,13 @@ constexpr int kRowWindow = GUDNI_ROW_WINDOW;   // power of two
 struct AccumScratch {
     uint32_t rows[kRowWindow][32];
 };
-__device__ __forceinline__ void accumulateWarp(const FrameParams& P, AccumScratch& W, const gudni_tile& tile, unsigned unit, int column) {
+__device__ __forceinline__ void accumulateWarp(const FrameParams& P, AccumScratch& W, const gudni_tile& tile, const ThreadRec* recp, int column) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const ThreadGeom g = threadGeom(P, tile, column);
-    const ThreadRec rec = P.threadRecs[(size_t)unit * 32 + lane];
+    ThreadRec rec{};
+    rec.count = kRecInactive;
+    if (recp) rec = *recp;
     uint32_t* outp = P.out + (size_t)(g.originY - P.rowOrigin) * P.width + g.originX;   // only dereferenced when active
     const bool mine = rec.count != kRecInactive;
     bool done = !mine;
@@ -616,11 +619,12 @@ __device__ __forceinline__ void accumulateWarp(const FrameParams& P, AccumScratc
 
 // One warp, one (tile, 32-column group) of a dense tile WITH pictures: one pass over the unresolved streams,
 // every lane composites the sections of its own pixels.
-__device__ __forceinline__ void pictureWarp(const FrameParams& P, const TileTable& T, const gudni_tile& tile, unsigned unit, int column) {
+__device__ __forceinline__ void pictureWarp(const FrameParams& P, const TileTable& T, const gudni_tile& tile, const ThreadRec* recp, int column) {
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
     const ThreadGeom g = threadGeom(P, tile, column);
-    const ThreadRec rec = P.threadRecs[(size_t)unit * 32 + lane];
+    ThreadRec rec{};
+    rec.count = kRecInactive;
+    if (recp) rec = *recp;
     const float4 bgPremul = premultiply(P.background);
     uint32_t* outp = P.out + (size_t)(g.originY - P.rowOrigin) * P.width + g.originX;
     ShapeStack base{rec.lo, rec.hi}, cur{rec.lo, rec.hi};

@@ -52,11 +52,13 @@ __device__ __forceinline__ int packWarp(const FrameParams& P, GenQueue& q, const
             const int threadId = P.tileThreadBase[tileIndex] + column;
             if (P.dbgThresholds) P.dbgThresholds[threadId] = q.len;
             if (P.dbgShapeBits) P.dbgShapeBits[threadId] = (int32_t)bits;
-#ifdef GUDNI_GEN_SORT_BINARY
-            sortQueueBinary(q);
-#else
-            sortQueue(q);
+            // a long queue mostly lives in local memory, where the linear scan of the plain insertion sort is a chain
+            // of dependent loads per element; the binary search + block move has O(log n) of those
+#ifndef GUDNI_GEN_SORT_BINARY_FROM
+#define GUDNI_GEN_SORT_BINARY_FROM 12
 #endif
+            if (q.len > GUDNI_GEN_SORT_BINARY_FROM) sortQueueBinary(q);
+            else sortQueue(q);
             count = q.len;
         }
     }

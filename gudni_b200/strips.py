@@ -190,6 +190,21 @@ class StripRenderer:
         self.r.frame_target(None)
 
     # -- one frame ---------------------------------------------------------------------------------
+    def render_to_host(self, frame, host_canvas):
+        """The host-presenter path: this rank rasterizes its strip from host buffers and copies it over its own
+        PCIe link straight into its rows of `host_canvas` (a (H, W) uint32 array every rank maps — POSIX shared
+        memory, page-locked by each rank).  No inter-GPU traffic; the caller's barrier closes the frame."""
+        r = self.r
+        rows = self.my_rows
+        if rows[1] <= rows[0]:
+            return
+        r.frame_target(None)
+        r.frame_begin(self.scene, frame)
+        if self.world > 1:
+            r.frame_strip(*rows)
+        r.raster_entries(self.entries)
+        _, self.last_stats = r.frame_end(out=host_canvas[rows[0]:rows[1]])
+
     def render(self, frame=0, dscene=None):
         """Rasterize this rank's strip and gather.  Returns the canvas tensor on the presenting rank."""
         r, torch = self.r, self.torch

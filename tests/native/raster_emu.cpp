@@ -93,6 +93,7 @@ using namespace gudni_dev;
 static size_t g_storeEntriesOverride;
 static size_t g_streamChunksOverride;
 static size_t g_refSlabsOverride;
+static int g_laneShift;
 static int g_rowBegin = 0, g_rowEnd = 0;    // raster_emu_set_strip: rows of the canvas this "context" renders (0,0 = all)
 namespace {
 
@@ -151,6 +152,7 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
     P.strandBounds = bounds.data();
     P.tileOrder = order.data();
     P.numStreams = std::max(1, std::min(3, nTiles));
+    P.laneShift = g_laneShift;
     // section-stream pool (raster_split.cuh): generous (the shim sizes it from the last frame's demand and retries a frame that ran dry), or what raster_emu_set_stream_chunks forces
     const size_t chunks = g_streamChunksOverride ? g_streamChunksOverride
                                                  : std::max<size_t>(threads * 96 + (size_t)in.width * in.height / 16, (size_t)1 << 14);
@@ -270,6 +272,8 @@ void raster_emu_set_store_entries(size_t n) { g_storeEntriesOverride = n; }
 void raster_emu_set_stream_chunks(size_t n) { g_streamChunksOverride = n; }
 // ... and for the table of distinct shape stacks (slabs of 128 numbers)
 void raster_emu_set_ref_slabs(size_t n) { g_refSlabsOverride = n; }
+// the render kernels' units are 32 >> shift column-threads wide (what the shim picks for launches of few tiles)
+void raster_emu_set_lane_shift(int shift) { g_laneShift = shift; }
 
 // order in which the emulator runs the threads of a CTA between rendezvous points (see runBlock)
 void raster_emu_set_schedule(int mode) { cuemu::scheduleMode = mode; }

@@ -389,6 +389,18 @@ def test_kernel_variant_small_tables():
     run(L, scenes.picture_scene(320, 300, flowers_size=(350, 200)))
 
 
+@pytest.mark.parametrize("shift", [1, 2])
+def test_units_narrower_than_a_warp(emu, shift):
+    """Launches of few tiles are dealt out in units of 16 or 8 column-threads (forEachUnit): same bits."""
+    emu.raster_emu_set_lane_shift(shift)
+    try:
+        run(emu, scenes.fuzzy_circles(150, 200, 150, 4, 40, 6))
+        run(emu, scenes.picture_scene(320, 300, flowers_size=(350, 200)))
+        run(emu, scenes.thin_rectangles(60, width=64, spacing=3.0, thickness=1.3))
+    finally:
+        emu.raster_emu_set_lane_shift(0)
+
+
 def test_device_derived_spec(emu, emu_scene):
     """The RasterSpec the reference would derive from the B200's OpenCL device (1,024-pixel tiles, 1,024 threads
     per tile, MAXTHRESHOLDS 2,853 — tests/test_reference_pin.py): 32 warps per tile, 1,024-pixel root tiles."""
