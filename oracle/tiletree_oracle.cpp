@@ -6,10 +6,13 @@
 //       /root/reference/src/Graphics/Gudni/Raster/TileTree.hs:74-204
 //   accumulateRasterJobs / addTileToRasterJob   Raster/Job.hs:121-178
 //   buildRasterJobs (argument swap and job-list order)   OpenCL/CallKernels.hs:244-255
-// PARITY UNPINNED for this file: the reference holds no fixtures for the tile tree and, unlike the kernel
-// file (oracle/refbuild/), its Haskell source cannot be compiled in this image.  Checked by invariants
-// (every pixel in exactly one leaf, caps respected unless at the 8-pixel floor, shape order) and, end to
-// end, by images: a wrong tile assignment shows up as wrong pixels against oracle/_ref.
+// How this file is pinned: the reference holds no fixtures for the tile tree and its Haskell cannot be compiled in
+// this image, so tests/golden/tiletree_handworked.py derives six inputs by hand from TileTree.hs / Job.hs /
+// CallKernels.hs, rule by rule with line citations (strict comparisons at a cut, the 127th shape splitting across then
+// along, the strand cap, the 8-pixel floor keeping 130 shapes, a split child that splits again while being refilled,
+// job packing with the swapped arguments); tests/test_tiletree_handworked.py holds this file to those literals and
+// tests/test_gpu_tiletree_handworked.py the GPU binning.  Beyond them: invariants (every pixel in exactly one leaf, caps
+// respected unless at the floor, shape order) and, end to end, images against oracle/_ref.
 #include <cstdint>
 #include <cstring>
 #include <memory>

@@ -85,3 +85,15 @@ def test_bad_indices_are_refused(rasterizer):
         rasterizer.raster_outlines(0, scene)
     img, _ = rasterizer.raster_scene(1, scenes.tiny_square())     # the context is still usable
     assert img.shape == (16, 16)
+
+
+def test_hand_worked_outlines(rasterizer):
+    """The GPU strand kernels against the fixtures derived by hand from Raster/Strand.hs, Deknob.hs and ReorderTable.hs
+    (tests/golden/strands_handworked.py): knob split, last run first, reversed runs, a run of 17 cut at 16, tree order."""
+    from golden.strands_handworked import CASES
+    from test_strands_handworked import check as check_fixture, scene_of
+    for name in sorted(CASES):
+        scene = scene_of(CASES[name])
+        rasterizer.raster_outlines(0, scene)
+        geometry, entries = rasterizer.debug_strands()
+        check_fixture(CASES[name], geometry, entries)
