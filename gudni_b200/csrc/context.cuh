@@ -69,7 +69,7 @@ struct gudni_ctx {
     unsigned long long streamDemand = 0;  // chunks the slice kernel drew last frame
     // resident CTAs per SM of the persistent kernels on this context's device
     bool occupancyKnown = false;
-    int genCtasPerSm = 0, sliceCtasPerSm = 0, colorCtasPerSm = 0, numSms = 0;
+    int genCtasPerSm = 0, sortCtasPerSm = 0, sliceCtasPerSm = 0, colorCtasPerSm = 0, numSms = 0;
     int resolveCtasPerSm = 0, compositeCtasPerSm = 0, accumulateCtasPerSm = 0;
     DevBuf stackKeys, stackColors, refSlabs;   // the frame's table of distinct shape stacks
     unsigned long long refCapSlabs = 0;

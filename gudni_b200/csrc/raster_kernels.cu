@@ -4,6 +4,7 @@
 
 #include <algorithm>
 
+#include "raster_sort.cuh"
 #include "raster_split.cuh"
 
 using namespace gudni_dev;
@@ -21,10 +22,11 @@ using namespace gudni_dev;
 constexpr int kSliceWarpsPerCta = GUDNI_SLICE_WARPS;
 constexpr int kColorWarpsPerCta = GUDNI_COLOR_WARPS;
 
-// A frame (or a launch of up to kLaunchTiles tiles of it) goes through six kernels on one stream; every one sizes
+// A frame (or a launch of up to kLaunchTiles tiles of it) goes through seven kernels on one stream; every one sizes
 // its grid to what the chip holds resident and pulls its work from a global counter, expensive tiles first:
-//   raster_generate_kernel    generateThresholds + sortThresholds (K.cl:2030-2115), one CTA per tile: sorted
-//                             threshold queues packed into HBM (20 B per threshold)
+//   raster_generate_kernel    generateThresholds (K.cl:2030-2082), one CTA per tile: the column-threads' threshold
+//                             queues packed into HBM (20 B per threshold)
+//   raster_sort_kernel        sortThresholds (K.cl:2084-2115): a warp rank-sorts the 32 queues of a unit in place
 //   raster_slice_kernel       the state machine of renderThresholds (K.cl:2117-2167) without colours: one
 //                             section stream per column-thread
 //   raster_resolve_kernel     the streams' shape stacks numbered (deduplicated per warp)
@@ -41,7 +43,7 @@ __device__ __forceinline__ void registerSpill(const FrameParams& P, int tileInde
         P.spillList[slot] = ((unsigned long long)tileIndex << 32) | (unsigned long long)column;
 }
 
-// generateThresholds + sortThresholds (K.cl:2030-2115), one CTA per tile: blockDim.x = threadsPerTile, thread =
+// generateThresholds (K.cl:2030-2082), one CTA per tile: blockDim.x = threadsPerTile, thread =
 // column-thread.  Dynamic shared memory: the tile's staged strand headers, then one queue window per warp.
 __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams P, int tileBase, int nTiles) {
 #ifdef GUDNI_HOST_EMULATION
@@ -105,6 +107,13 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
     }
 }
 
+// sortThresholds (K.cl:2084-2115): the 32 queues of a unit rank-sorted by one warp (raster_sort.cuh).
+#ifndef GUDNI_SORT_WARPS
+#define GUDNI_SORT_WARPS 4
+#endif
+constexpr int kSortWarpsPerCta = GUDNI_SORT_WARPS;
+__global__ void __launch_bounds__(kSortWarpsPerCta * 32) raster_sort_kernel(const FrameParams P, int tileBase, int nTiles);
+
 // The sweep's state machine alone (raster_split.cuh): sorted thresholds in, section streams out.
 #ifndef GUDNI_SLICE_MIN_CTAS
 #define GUDNI_SLICE_MIN_CTAS 8      // 64 registers: 32 warps per SM hide the divergent kernel's latencies (96 registers / 20 warps: +1.1 ms on S4)
@@ -137,6 +146,15 @@ __device__ __forceinline__ void forEachUnit(const FrameParams& P, int tileBase, 
         ThreadRec* rec = lane < lanesPerUnit ? P.threadRecs + (((size_t)tileIndex << P.computeDepth) + (size_t)column) : nullptr;
         body(tileIndex, tile, rec, column);
     }
+}
+
+__global__ void __launch_bounds__(kSortWarpsPerCta * 32) raster_sort_kernel(const FrameParams P, int tileBase, int nTiles) {
+    __shared__ SortScratch scratch[kSortWarpsPerCta];
+    SortScratch& W = scratch[threadIdx.x >> 5];
+    forEachUnit(P, tileBase, nTiles, kCntWorkSort, [&](int, const gudni_tile&, ThreadRec* rec, int) {
+        sortWarp(P, W, rec);
+        __syncwarp();
+    });
 }
 
 __global__ void __launch_bounds__(kSliceWarpsPerCta * 32, GUDNI_SLICE_MIN_CTAS) raster_slice_kernel(const FrameParams P, int tileBase, int nTiles) {
@@ -383,6 +401,10 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
                                                  (int)std::min<size_t>(genSmemMax, (size_t)227 * 1024)));
         GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->genCtasPerSm, raster_generate_kernel,
                                                                           ctx->spec.threads_per_tile, genSmem));
+        GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_sort_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sortCtasPerSm, raster_sort_kernel,
+                                                                          kSortWarpsPerCta * 32, 0));
+        ctx->sortCtasPerSm = std::max(ctx->sortCtasPerSm, 1);
         GUDNI_CUDA_TRY(ctx, cudaFuncSetAttribute(raster_slice_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         GUDNI_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->sliceCtasPerSm, raster_slice_kernel,
                                                                           kSliceWarpsPerCta * 32, 0));
@@ -411,6 +433,7 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkGenerate, 0, 8, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkColor, 0, 8, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkResolve, 0, 24, ctx->stream));
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkSort, 0, 8, ctx->stream));
     // units narrower than a warp when whole-warp units would not go round (see forEachUnit)
     long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
     P.laneShift = 0;
@@ -421,6 +444,8 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     tile_order_kernel<<<1, 1024, 0, ctx->stream>>>(const_cast<gudni_tile*>(P.tiles), tileBase, nTiles, const_cast<uint32_t*>(P.tileOrder), P.counters);
     ctx->launches++;
     raster_generate_kernel<<<std::min(ctx->genCtasPerSm * numSms, nTiles), ctx->spec.threads_per_tile, genSmem, ctx->stream>>>(P, tileBase, nTiles);
+    ctx->launches++;
+    raster_sort_kernel<<<grid(ctx->sortCtasPerSm, kSortWarpsPerCta), kSortWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
     ctx->launches++;
     raster_slice_kernel<<<grid(ctx->sliceCtasPerSm, kSliceWarpsPerCta), kSliceWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
     raster_resolve_kernel<<<grid(ctx->resolveCtasPerSm, kResolveWarpsPerCta), kResolveWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);

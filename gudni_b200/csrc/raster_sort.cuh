@@ -1,0 +1,132 @@
+// raster_sort.cuh — sortThresholds (Kernels.cl:2084-2115) as a warp-cooperative rank sort.
+//
+// The reference bubble-sorts every column-thread's threshold array in place in global memory (K.cl:1932-1976), one
+// work-item per array.  Round 1 and the first half of round 2 did the same thing lane-privately inside the generate
+// kernel (insertion sort where the queue was built: four slots in shared memory, the rest in local memory), which is
+// a chain of dependent local-memory round trips per element moved — on S5 (256-row column-threads, queues of a
+// hundred thresholds) more than half of the generate kernel's samples.
+//
+// Here the generate kernel packs the queues UNSORTED, in the order they were built, and a warp sorts the 32 queues
+// of a (tile, 32-column) unit together: the queues are staged in shared memory, every lane takes elements of the
+// flattened list and counts, for its element, the elements of the same queue that sort before it — the element's
+// rank — and the element is written straight to its final place in the store.  No element is moved twice, no lane
+// waits on another lane's memory, and the comparison count (sum of n^2) is spread over 32 lanes.
+//
+// The order is the reference's: `isBelow` (thresholdIsBelow, K.cl:1079-1094: top, then x at the top, then inverse
+// slope) with ties keeping the order in which the queue was built — what a stable insertion sort over the same
+// predicate gives (sortQueue), which is what the bubble sort of K.cl:1962-1976 gives.  For keys without NaN the
+// predicate is a strict weak order, so ranks are a permutation.  A queue that holds a NaN key is sorted by its own
+// lane with the sequential insertion sort instead (the order then depends on the comparison sequence).
+#pragma once
+#include "raster_warp.cuh"
+
+namespace gudni_dev {
+
+#ifndef GUDNI_SORT_CAP
+#define GUDNI_SORT_CAP 256
+#endif
+constexpr int kSortCap = GUDNI_SORT_CAP;   // thresholds staged at a time; at least kQueueCap so that any one queue fits
+static_assert(kSortCap >= kQueueCap, "a whole queue must fit the staging area");
+
+static_assert(kSortCap < 2048, "staged indices are packed into 11 bits");
+
+struct SortScratch {
+    float4 key[kSortCap];       // (top, x at the top, inverse slope, header bits): what isBelow compares, one 16-byte load
+    float4 thr[kSortCap];       // (top, bottom, left, right)
+    uint32_t info[kSortCap];    // lane | first staged index of the element's queue << 5 | queue length << 16
+    unsigned int first[33];     // staged index of each lane's first element (exclusive scan of the lengths)
+    unsigned int offset[32];    // each lane's place in the store
+    unsigned int nanMask;       // lanes whose queue holds a NaN key
+};
+
+// the queue as it lies in the store, for the sequential fallback
+struct StoreQueue {
+    float4* thr;
+    uint32_t* hdr;
+    int len;
+    __device__ __forceinline__ Thr getT(int i) const { const float4 v = thr[i]; return Thr{v.x, v.y, v.z, v.w}; }
+    __device__ __forceinline__ uint32_t getH(int i) const { return hdr[i]; }
+    __device__ __forceinline__ void set(int i, uint32_t h, const Thr& t) { thr[i] = make_float4(t.top, t.bottom, t.left, t.right); hdr[i] = h; }
+};
+
+// isBelow on staged keys: a sorts strictly after b
+__device__ __forceinline__ bool keyBelow(const float4& a, const float4& b) {
+    return (a.x > b.x) || ((a.x == b.x) && ((a.y > b.y) || ((a.y == b.y) && (a.z > b.z))));
+}
+
+// One warp, the queues of one unit.  `recp`: the lane's thread record (null: no column-thread in this lane).
+__device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, const ThreadRec* recp) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned int count = 0u, offset = 0u;
+    if (recp) {
+        const unsigned int c = recp->count;
+        if (c != kRecInactive) { count = c; offset = recp->offset; }
+    }
+    if (!__any_sync(full, count > 1u)) return;
+    bool sequential = false;   // this lane's queue holds a NaN key
+    int laneBegin = 0;
+    while (laneBegin < 32) {
+        // ---- the batch: consecutive lanes from laneBegin whose queues fit the staging area together ----------
+        unsigned int incl = lane >= laneBegin ? count : 0u;
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int v = __shfl_up_sync(full, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const unsigned fits = __ballot_sync(full, lane >= laneBegin && incl <= (unsigned int)kSortCap) >> laneBegin;
+        // lanes laneBegin .. laneEnd-1 (at least one: a single queue always fits)
+        const int laneEnd = fits == (full >> laneBegin) ? 32 : laneBegin + __ffs((int)~fits) - 1;
+        const bool inBatch = lane >= laneBegin && lane < laneEnd;
+        const unsigned int total = __shfl_sync(full, incl, laneEnd - 1);
+        __syncwarp();
+        W.first[lane] = inBatch ? incl - count : total;
+        W.offset[lane] = offset;
+        if (lane == 0) { W.first[32] = total; W.nanMask = 0u; }
+        __syncwarp();
+        // ---- stage: the batch's thresholds, flattened; coalesced within a queue ------------------------------------
+        for (unsigned int f = lane; f < total; f += 32) {
+            // the queue element f belongs to: the last lane of the batch whose first index is <= f
+            int lo = laneBegin, hi = laneEnd - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (W.first[mid] <= f) lo = mid; else hi = mid - 1;
+            }
+            const unsigned int qs = W.first[lo], n = W.first[lo + 1 < laneEnd ? lo + 1 : 32] - qs;
+            const unsigned int src = W.offset[lo] + (f - qs);
+            const float4 t = P.thrStore[src];
+            const uint32_t h = P.hdrStore[src];
+            const Thr th{t.x, t.y, t.z, t.w};
+            const float4 k = make_float4(t.x, tTopX(h, th), invSlope(h, th), __uint_as_float(h));
+            W.thr[f] = t;
+            W.key[f] = k;
+            W.info[f] = (uint32_t)lo | (qs << 5) | (n << 16);
+            // a NaN anywhere in a queue: that queue's lane sorts it sequentially (the order then depends on the comparison sequence)
+            if ((k.x != k.x) || (k.y != k.y) || (k.z != k.z)) atomicOr(&W.nanMask, 1u << lo);
+        }
+        __syncwarp();
+        const unsigned int owners = W.nanMask;
+        sequential = sequential || ((owners >> lane) & 1u);
+        // ---- rank + place ------------------------------------------------------------------------------------------------
+        for (unsigned int f = lane; f < total; f += 32) {
+            const uint32_t inf = W.info[f];
+            const unsigned int q = inf & 31u, qs = (inf >> 5) & 0x7FFu, n = inf >> 16;
+            if ((owners >> q) & 1u) continue;
+            const float4 me = W.key[f];
+            const unsigned int e = f - qs;
+            unsigned int rank = 0u;
+            for (unsigned int j = 0; j < e; j++) rank += keyBelow(W.key[qs + j], me) ? 0u : 1u;      // not after me and built before me
+            for (unsigned int j = e + 1; j < n; j++) rank += keyBelow(me, W.key[qs + j]) ? 1u : 0u;  // I am strictly after it
+            const unsigned int dst = W.offset[q] + rank;
+            P.thrStore[dst] = W.thr[f];
+            P.hdrStore[dst] = __float_as_uint(me.w);
+        }
+        __syncwarp();
+        laneBegin = laneEnd;
+    }
+    if (sequential && count > 1u) {
+        StoreQueue q{P.thrStore + offset, P.hdrStore + offset, (int)count};
+        sortQueue(q);
+    }
+}
+
+}  // namespace gudni_dev

@@ -26,9 +26,9 @@ constexpr int kStoreSlack = GUDNI_STORE_SLACK;   // free store entries in front 
 typedef HeadQueue<kQueueCap, kQueueHot> LaneQueue;
 
 // ---- sort + pack -----------------------------------------------------------------------------------
-// Every lane sorts the threshold queue of its column-thread (K.cl:2084-2115) where it was built, then the
-// warp packs the queues into the frame-wide store with one atomic (a warp prefix sum gives each lane its
-// offset).  Returns per lane 1 if the thread must be replayed against the HBM queue.
+// The warp packs the threshold queues of its column-threads, in the order they were built, into the frame-wide
+// store with one atomic (a warp prefix sum gives each lane its offset); raster_sort_kernel sorts them there
+// (K.cl:2084-2115).  Returns per lane 1 if the thread must be replayed against the HBM queue.
 struct GenScratch {
     float4 qThr[kGenQueueHot * 32];
     uint32_t qHdr[kGenQueueHot * 32];
@@ -52,13 +52,7 @@ __device__ __forceinline__ int packWarp(const FrameParams& P, GenQueue& q, const
             const int threadId = P.tileThreadBase[tileIndex] + column;
             if (P.dbgThresholds) P.dbgThresholds[threadId] = q.len;
             if (P.dbgShapeBits) P.dbgShapeBits[threadId] = (int32_t)bits;
-            // a long queue mostly lives in local memory, where the linear scan of the plain insertion sort is a chain
-            // of dependent loads per element; the binary search + block move has O(log n) of those
-#ifndef GUDNI_GEN_SORT_BINARY_FROM
-#define GUDNI_GEN_SORT_BINARY_FROM 12
-#endif
-            if (q.len > GUDNI_GEN_SORT_BINARY_FROM) sortQueueBinary(q);
-            else sortQueue(q);
+            // the queue leaves in the order it was built; raster_sort_kernel sorts it in the store (raster_sort.cuh)
             count = q.len;
         }
     }

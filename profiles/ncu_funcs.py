@@ -1,10 +1,10 @@
 """Aggregate an ncu source-level profile by enclosing function (found by scanning the CUDA sources for
-`__device__` / `__global__` / struct headers).  usage: python profiles/ncu_funcs.py report.ncu-rep [kernel index]"""
+`__device__` / `__global__` / struct headers).  usage: python profiles/ncu_funcs.py report.ncu-rep [kernel name regex]"""
 import csv, os, re, subprocess, sys
 rep = sys.argv[1]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] +
-                     (["--kernel-id", f":::{sys.argv[2]}"] if len(sys.argv) > 2 else []), capture_output=True, text=True).stdout
+                     (["--kernel-name", f"regex:{sys.argv[2]}"] if len(sys.argv) > 2 else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 marks = {}
 def funcs(path):
@@ -32,7 +32,7 @@ hdr = None; cur = ""; agg = {}
 for r in rows:
     if len(r) == 2 and r[0] == "File Path": cur = r[1]; continue
     if r and r[0] == "Line No": hdr = r; continue
-    if hdr and r and r[0].isdigit() and len(r) == len(hdr):
+    if hdr and r and r[0].isdigit() and len(r) >= 9:
         d = dict(zip(hdr[4:], r[4:]))
         if not d["# Samples"].isdigit(): continue
         a = agg.setdefault(where(cur, int(r[0])), [0, 0, 0])

@@ -8,7 +8,7 @@ hdr = None; lines = []; cur_file = ""
 for r in rows:
     if len(r) == 2 and r[0] == "File Path": cur_file = r[1].split("/")[-1]; continue
     if r and r[0] == "Line No": hdr = r; continue
-    if hdr and r and r[0].isdigit() and len(r) == len(hdr):
+    if hdr and r and r[0].isdigit() and len(r) >= 9:
         d = dict(zip(hdr[4:], r[4:]))
         if not d["# Samples"].isdigit(): continue
         lines.append((cur_file, int(r[0]), r[1].strip()[:90], int(d["# Samples"]), int(d["Instructions Executed"]), int(d["Thread Instructions Executed"]), d))

@@ -175,6 +175,7 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
                           static_cast<const uint8_t*>(boundsRecords), boundsStride, (int)nBoundsRecords, bounds.data(), counters.data());
         cuemu::launch(tile_order_kernel, dim3(1), dim3(256), tilesCopy.data(), 0, nTiles, order.data(), counters.data());
         cuemu::launch(raster_generate_kernel, dim3(2), dim3(in.spec->threads_per_tile), P, 0, nTiles);
+        cuemu::launch(raster_sort_kernel, dim3(2), dim3(kSortWarpsPerCta * 32), P, 0, nTiles);
         cuemu::launch(raster_slice_kernel, dim3(2), dim3(kSliceWarpsPerCta * 32), P, 0, nTiles);
         cuemu::launch(raster_resolve_kernel, dim3(2), dim3(kResolveWarpsPerCta * 32), P, 0, nTiles);
         cuemu::launch(raster_composite_kernel, dim3(2), dim3(kCompositeWarpsPerCta * 32), P);
