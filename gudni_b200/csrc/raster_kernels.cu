@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
 
 // sortThresholds (K.cl:2084-2115): the 32 queues of a unit rank-sorted by one warp (raster_sort.cuh).
 #ifndef GUDNI_SORT_WARPS
-#define GUDNI_SORT_WARPS 4
+#define GUDNI_SORT_WARPS 2
 #endif
 constexpr int kSortWarpsPerCta = GUDNI_SORT_WARPS;
 __global__ void __launch_bounds__(kSortWarpsPerCta * 32) raster_sort_kernel(const FrameParams P, int tileBase, int nTiles);

@@ -29,6 +29,13 @@ constexpr int kSortCap = GUDNI_SORT_CAP;   // thresholds staged at a time; at le
 static_assert(kSortCap >= kQueueCap, "a whole queue must fit the staging area");
 
 static_assert(kSortCap < 2048, "staged indices are packed into 11 bits");
+#ifndef GUDNI_SORT_LONG
+#define GUDNI_SORT_LONG 64
+#endif
+// Ranking costs n^2 comparisons per queue; a queue longer than this is sorted on its own by the whole warp with a
+// bitonic network over a permutation in shared memory instead (n log^2 n; the keys stay where they were staged and
+// the element index breaks ties, which makes the order total and therefore the same stable order).
+constexpr unsigned int kSortLong = GUDNI_SORT_LONG;
 
 struct SortScratch {
     float4 key[kSortCap];       // (top, x at the top, inverse slope, header bits): what isBelow compares, one 16-byte load
@@ -51,7 +58,57 @@ struct StoreQueue {
 
 // isBelow on staged keys: a sorts strictly after b
 __device__ __forceinline__ bool keyBelow(const float4& a, const float4& b) {
-    return (a.x > b.x) || ((a.x == b.x) && ((a.y > b.y) || ((a.y == b.y) && (a.z > b.z))));
+    return (bool)((int)(a.x > b.x) | ((int)(a.x == b.x) & ((int)(a.y > b.y) | ((int)(a.y == b.y) & (int)(a.z > b.z)))));
+}
+
+// One warp, one long queue (n > kSortLong) at store[offset ...].  Returns false (nothing written) if a key is NaN.
+__device__ __forceinline__ bool sortLongQueue(const FrameParams& P, SortScratch& W, unsigned int offset, unsigned int n) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned int size = 128;
+    while (size < n) size <<= 1;                 // n <= kQueueCap <= kSortCap
+    uint32_t* perm = W.info;
+    bool nan = false;
+    __syncwarp();
+    for (unsigned int f = lane; f < size; f += 32) {
+        perm[f] = f;
+        if (f < n) {
+            const float4 t = P.thrStore[offset + f];
+            const uint32_t h = P.hdrStore[offset + f];
+            const Thr th{t.x, t.y, t.z, t.w};
+            const float4 k = make_float4(t.x, tTopX(h, th), invSlope(h, th), __uint_as_float(h));
+            W.thr[f] = t;
+            W.key[f] = k;
+            nan = nan || (k.x != k.x) || (k.y != k.y) || (k.z != k.z);
+        }
+    }
+    if (__any_sync(full, nan)) return false;
+    __syncwarp();
+    // a precedes b: indices >= n are padding and sort last; equal keys keep the order of their indices
+    auto precedes = [&](unsigned int a, unsigned int b) -> bool {
+        if (a >= n || b >= n) return a < b;
+        const float4 ka = W.key[a], kb = W.key[b];
+        const bool bAfterA = keyBelow(kb, ka), aAfterB = keyBelow(ka, kb);
+        return bAfterA || (!aAfterB && (a < b));
+    };
+    for (unsigned int k = 2; k <= size; k <<= 1) {
+        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned int p = lane; p < (size >> 1); p += 32) {
+                const unsigned int i = ((p & ~(j - 1u)) << 1) | (p & (j - 1u)), l = i | j;
+                const unsigned int a = perm[i], b = perm[l];
+                const bool ascending = (i & k) == 0u;
+                if (ascending ? precedes(b, a) : precedes(a, b)) { perm[i] = b; perm[l] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    for (unsigned int r = lane; r < n; r += 32) {
+        const unsigned int e = perm[r];
+        P.thrStore[offset + r] = W.thr[e];
+        P.hdrStore[offset + r] = __float_as_uint(W.key[e].w);
+    }
+    __syncwarp();
+    return true;
 }
 
 // One warp, the queues of one unit.  `recp`: the lane's thread record (null: no column-thread in this lane).
@@ -65,6 +122,15 @@ __device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, c
     }
     if (!__any_sync(full, count > 1u)) return;
     bool sequential = false;   // this lane's queue holds a NaN key
+    // long queues first, one at a time
+    const bool isLong = count > kSortLong;
+    for (unsigned longLanes = __ballot_sync(full, isLong); longLanes; longLanes &= longLanes - 1u) {
+        const int l = __ffs((int)longLanes) - 1;
+        const bool sorted = sortLongQueue(P, W, __shfl_sync(full, offset, l), __shfl_sync(full, count, l));
+        if (!sorted && lane == l) sequential = true;
+    }
+    if (isLong) count = 0u;    // (done, or left to the sequential sort below)
+    const unsigned int ownCount = isLong ? recp->count : count;
     int laneBegin = 0;
     while (laneBegin < 32) {
         // ---- the batch: consecutive lanes from laneBegin whose queues fit the staging area together ----------
@@ -123,8 +189,8 @@ __device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, c
         __syncwarp();
         laneBegin = laneEnd;
     }
-    if (sequential && count > 1u) {
-        StoreQueue q{P.thrStore + offset, P.hdrStore + offset, (int)count};
+    if (sequential && ownCount > 1u) {
+        StoreQueue q{P.thrStore + offset, P.hdrStore + offset, (int)ownCount};
         sortQueue(q);
     }
 }

@@ -25,6 +25,21 @@ def test_long_queues_stay_on_chip(rasterizer):
     level2_parity(rasterizer, scene, ref=ref)
 
 
+def test_queues_of_two_hundred_take_the_bitonic_network(rasterizer):
+    scene = scenes.thin_rectangles(100, width=64, spacing=2.0, thickness=0.9)
+    img, stats, ref = level1_parity(rasterizer, scene)
+    assert max(int(c.max()) for c in ref.n_thresholds) > 128
+    assert stats.n_spilled_threads == 0 and stats.n_overflow_threads == 0
+
+
+@pytest.mark.parametrize("n", [12, 50, 100])
+def test_equal_sort_keys_keep_build_order(rasterizer, n):
+    """Queues full of thresholds that tie in all three sort keys (n copies of one shape): the rank sort and the
+    bitonic network must leave them in the order the reference's bubble sort does."""
+    from test_kernels_emulated import identical_shapes
+    level1_parity(rasterizer, identical_shapes(n))
+
+
 def test_very_long_queues_take_the_replay_path(rasterizer):
     # one shape of 150 thin rectangles on a 256-wide tile: every column-thread is 256 rows tall and crosses
     # ~300 thresholds, over the 256-entry on-chip capacity, under MAXTHRESHOLDS

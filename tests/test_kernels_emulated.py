@@ -150,6 +150,29 @@ def test_queue_leaves_the_shared_memory_window(emu):
     assert stats[1] == 0                      # > 64 thresholds per column, still on chip
 
 
+def identical_shapes(n, width=48, height=40):
+    """n copies of one rotated rectangle, each its own shape: every column's queue holds runs of thresholds whose
+    sort keys are equal in all three components, so the order among them is the order they were built in."""
+    from gudni_b200.scene import SceneBuilder
+    b = SceneBuilder(width, height, (1.0, 1.0, 1.0, 1.0), name=f"identical-{n}")
+    for i in range(n):
+        b.rectangle(b.solid(0.1 + 0.8 * (i % 7) / 7.0, 0.5, 0.9 - 0.8 * (i % 5) / 5.0, 0.35), 20.3, 25.7,
+                    [("translate", 9.2, 6.1), ("rotate", 0.03)])
+    return b.freeze()
+
+
+@pytest.mark.parametrize("n", [12, 50, 100])
+def test_equal_keys_keep_the_order_they_were_built_in(emu, n):
+    """The rank sort (queues up to 64) and the bitonic network (longer ones) against the reference's bubble sort on
+    queues full of ties: 2 n thresholds per column, n of them equal to each other at the top edge."""
+    run(emu, identical_shapes(n))
+
+
+def test_long_queues_take_the_bitonic_network(emu):
+    stats = run(emu, scenes.thin_rectangles(100, width=64, spacing=2.0, thickness=0.9))
+    assert stats[1] == 0                      # 128 < thresholds per column <= 256, still on chip
+
+
 def test_replay_of_spilled_threads(emu):
     """Queues past the on-chip capacity of 256, and tiles with more shapes than stack bits at the 8-pixel
     floor: both go through the lane-private HBM-queue replay kernel."""
