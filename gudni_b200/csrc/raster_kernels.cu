@@ -163,10 +163,9 @@ __global__ void __launch_bounds__(kSliceWarpsPerCta * 32, GUDNI_SLICE_MIN_CTAS) 
     SliceScratch& W = scratch[warp];
     if (lane == 0) { W.slabNext = 0u; W.slabEnd = 0u; }
     __syncwarp();
-    LaneQueue q;
-    q.limit = min(kQueueCap, P.maxThresholds);
-    q.thrHot = W.qThr + lane;
-    q.hdrHot = W.qHdr + lane;
+    ActiveRun q;
+    q.thr = W.aThr + lane;
+    q.hdr = W.aHdr + lane;
     forEachUnit(P, tileBase, nTiles, kCntWorkSweep, [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
         const unsigned int count = rec ? rec->count : 0u;
         bool exhausted = false;

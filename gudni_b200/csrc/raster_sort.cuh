@@ -15,8 +15,9 @@
 // The order is the reference's: `isBelow` (thresholdIsBelow, K.cl:1079-1094: top, then x at the top, then inverse
 // slope) with ties keeping the order in which the queue was built — what a stable insertion sort over the same
 // predicate gives (sortQueue), which is what the bubble sort of K.cl:1962-1976 gives.  For keys without NaN the
-// predicate is a strict weak order, so ranks are a permutation.  A queue that holds a NaN key is sorted by its own
-// lane with the sequential insertion sort instead (the order then depends on the comparison sequence).
+// predicate is a strict weak order, so ranks are a permutation.  A queue that holds a NaN is sorted by its own lane
+// with the sequential insertion sort instead (the order then depends on the comparison sequence) and its thread is
+// flagged (kRecUnordered): the slice kernel hands it to the replay.
 #pragma once
 #include "raster_warp.cuh"
 
@@ -79,7 +80,7 @@ __device__ __forceinline__ bool sortLongQueue(const FrameParams& P, SortScratch&
             const float4 k = make_float4(t.x, tTopX(h, th), invSlope(h, th), __uint_as_float(h));
             W.thr[f] = t;
             W.key[f] = k;
-            nan = nan || (k.x != k.x) || (k.y != k.y) || (k.z != k.z);
+            nan = nan || (t.x != t.x) || (t.y != t.y) || (t.z != t.z) || (t.w != t.w) || (k.z != k.z);
         }
     }
     if (__any_sync(full, nan)) return false;
@@ -112,7 +113,7 @@ __device__ __forceinline__ bool sortLongQueue(const FrameParams& P, SortScratch&
 }
 
 // One warp, the queues of one unit.  `recp`: the lane's thread record (null: no column-thread in this lane).
-__device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, const ThreadRec* recp) {
+__device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, ThreadRec* recp) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     unsigned int count = 0u, offset = 0u;
@@ -120,7 +121,7 @@ __device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, c
         const unsigned int c = recp->count;
         if (c != kRecInactive) { count = c; offset = recp->offset; }
     }
-    if (!__any_sync(full, count > 1u)) return;
+    if (!__any_sync(full, count > 0u)) return;
     bool sequential = false;   // this lane's queue holds a NaN key
     // long queues first, one at a time
     const bool isLong = count > kSortLong;
@@ -167,7 +168,7 @@ __device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, c
             W.key[f] = k;
             W.info[f] = (uint32_t)lo | (qs << 5) | (n << 16);
             // a NaN anywhere in a queue: that queue's lane sorts it sequentially (the order then depends on the comparison sequence)
-            if ((k.x != k.x) || (k.y != k.y) || (k.z != k.z)) atomicOr(&W.nanMask, 1u << lo);
+            if ((t.x != t.x) || (t.y != t.y) || (t.z != t.z) || (t.w != t.w) || (k.z != k.z)) atomicOr(&W.nanMask, 1u << lo);
         }
         __syncwarp();
         const unsigned int owners = W.nanMask;
@@ -189,7 +190,9 @@ __device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, c
         __syncwarp();
         laneBegin = laneEnd;
     }
-    if (sequential && ownCount > 1u) {
+    if (sequential) {
+        // the slice kernel hands such a thread to the replay, which follows the reference's insertion sequence
+        const_cast<ThreadRec*>(recp)->pad1 = kRecUnordered;
         StoreQueue q{P.thrStore + offset, P.hdrStore + offset, (int)ownCount};
         sortQueue(q);
     }

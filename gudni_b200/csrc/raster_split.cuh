@@ -46,11 +46,82 @@ constexpr int kMaxPixelRun = 0xFFFF;
 constexpr unsigned int kSlabChunks = GUDNI_SLAB_CHUNKS;   // chunks a warp draws from the pool at a time
 constexpr unsigned int kSlabLow = 40;                      // refill when fewer are left at the top of a round
 
+// ---- the slice kernel's view of a column-thread's threshold queue ------------------------------------------------------
+// The reference keeps one sorted array per work-item and, every time a run of thresholds with the same top becomes
+// active, cuts each of them at the next event below (sliceActive, K.cl:1053-1067) and inserts the lower parts back
+// into the array behind the run (insertThreshold, K.cl:1105-1124) — every insertion moves the whole run.  The same
+// queue here is three pieces that are never copied into one another:
+//   * the ACTIVE RUN in shared memory (kActiveCap entries per lane, element-major / lane-minor).  An entry holds the
+//     threshold as it was before the cut — (bottom, left, right), the top being the run's — plus the x of the cut,
+//     from which both halves follow by selection: the upper part the band's sections are measured against, and the
+//     lower part;
+//   * the REMAINDERS: when the run ends its lower parts are written over it in place, in the order the reference's
+//     insertions would have left them (they all start at the cut: ordered by x there, then slope; a later one goes
+//     before an earlier one it ties with);
+//   * the rest of the sorted queue, read in order from the threshold store and never written.
+// The next run is the remainders merged with the store's thresholds that start at the same y (a remainder goes before
+// a stored threshold it ties with, as an insertion from the front would put it).  Numbers that break the order — a
+// NaN coordinate, produced or inherited — send the thread to the replay kernel, which follows the reference's
+// insertion sequence literally; so does a run of more than kActiveCap thresholds.
+#ifndef GUDNI_ACTIVE_CAP
+#define GUDNI_ACTIVE_CAP 12
+#endif
+constexpr int kActiveCap = GUDNI_ACTIVE_CAP;
+
 struct SliceScratch {
-    float4 qThr[kQueueHot * 32];     // head window of the 32 threshold queues
-    uint32_t qHdr[kQueueHot * 32];
+    float4 aThr[kActiveCap * 32];    // (bottom, left, right, x of the cut)
+    uint32_t aHdr[kActiveCap * 32];
     unsigned int slabNext, slabEnd;  // the warp's private range of pool chunks
     unsigned int pad[2];
+};
+
+struct ActiveRun {
+    float4* thr;            // this lane's column of SliceScratch::aThr: entry e at thr[e * 32]
+    uint32_t* hdr;
+    const float4* sThr;     // the thread's sorted queue in the store
+    const uint32_t* sHdr;
+    int sNext, sCount;      // stored thresholds not consumed yet: [sNext, sCount); element sNext is in `head`
+    float4 head;            // (top, bottom, left, right)
+    uint32_t headH;
+    float runTop, cutY;     // the active run's common top; where it was cut (the uppers' bottom)
+    int front;              // first entry of the run still active (zero-height ones in front are dropped, K.cl:1794-1799)
+    int rem;                // remainders waiting in thr[0 .. rem), all starting at remTop
+    float remTop;
+    bool bad;               // NaN or capacity: replay the thread
+    __device__ __forceinline__ void attach(const float4* t, const uint32_t* h, unsigned int offset, int count) {
+        sThr = t + offset; sHdr = h + offset; sNext = 0; sCount = count;
+        front = 0; rem = 0; remTop = FLT_MAX; runTop = 0.0f; cutY = 0.0f; bad = false;
+        head = make_float4(FLT_MAX, FLT_MAX, 0.f, 0.f); headH = 0u;
+        if (count > 0) { head = sThr[0]; headH = sHdr[0]; }
+    }
+    __device__ __forceinline__ bool haveHead() const { return sNext < sCount; }
+    __device__ __forceinline__ void advance() {
+        sNext++;
+        if (sNext < sCount) { head = sThr[sNext]; headH = sHdr[sNext]; }
+        else head.x = FLT_MAX;
+    }
+    // the upper part of entry e: what the reference's array holds at that index while the run is active
+    __device__ __forceinline__ void upper(int e, Thr& t, uint32_t& h) const {
+        const float4 v = thr[e * 32];
+        const uint32_t eh = hdr[e * 32];
+        const bool cut = (runTop < cutY) && (cutY < v.x);
+        const bool pos = hPositive(eh);
+        t.top = runTop;
+        t.bottom = cut ? cutY : v.x;
+        t.left = (cut && !pos) ? v.w : v.y;
+        t.right = (cut && pos) ? v.w : v.z;
+        h = (cut && !pos) ? (eh & ~kPersistBit) : eh;
+    }
+    __device__ __forceinline__ uint32_t upperHeader(int e) const {
+        const float bottom = thr[e * 32].x;
+        const uint32_t eh = hdr[e * 32];
+        const bool cut = (runTop < cutY) && (cutY < bottom);
+        return (cut && !hPositive(eh)) ? (eh & ~kPersistBit) : eh;
+    }
+    __device__ __forceinline__ float upperBottom(int e) const {
+        const float bottom = thr[e * 32].x;
+        return ((runTop < cutY) && (cutY < bottom)) ? cutY : bottom;
+    }
 };
 
 // Warp-converged: make sure the warp's slab holds at least `want` chunks (a lane that still runs dry inside a
@@ -102,46 +173,126 @@ struct StreamWriter {
     }
 };
 
+// The run has ended (its bottom is the band's): its lower parts replace it, in queue order (see ActiveRun).
+__device__ __forceinline__ void runToRemainders(ActiveRun& q, int numActive) {
+    const float top = q.runTop, cutY = q.cutY;
+    int m = 0;
+    for (int i = 0; i < numActive; i++) {
+        const float4 v = q.thr[(q.front + i) * 32];
+        const uint32_t h = q.hdr[(q.front + i) * 32];
+        if (!((top < cutY) && (cutY < v.x))) continue;                // not cut: it ends with the run
+        // splitThreshold / divideThreshold, K.cl:928-979: the lower part
+        const bool pos = hPositive(h);
+        const Thr lower = pos ? Thr{cutY, v.x, v.w, v.z} : Thr{cutY, v.x, v.y, v.w};
+        const uint32_t lh = pos ? (h & ~kPersistBit) : h;
+        if (!tKeep(lh, lower)) continue;
+        // insertThreshold (K.cl:1105-1124) walks from the front past everything the new one is strictly below and
+        // stops; in a sorted list that is: behind it stay exactly the entries it is not strictly below
+        int j = m;
+        while (j > 0) {
+            const float4 u = q.thr[(j - 1) * 32];
+            const uint32_t uh = q.hdr[(j - 1) * 32];
+            if (isBelow(lh, lower, uh, Thr{cutY, u.x, u.y, u.z})) break;
+            q.thr[j * 32] = u;
+            q.hdr[j * 32] = uh;
+            j--;
+        }
+        q.thr[j * 32] = make_float4(lower.bottom, lower.left, lower.right, 0.0f);
+        q.hdr[j * 32] = lh;
+        m++;
+    }
+    q.rem = m;
+    q.remTop = cutY;
+    q.front = 0;
+}
+
+// splitNext = countActive + nextSlicePoint + sliceActive (K.cl:1007-1077): the thresholds that start at the queue's
+// smallest top become the run and are cut at the next event.  Returns the slice point; numActive = 0 and q.bad set
+// if the run does not fit.
+__device__ __forceinline__ float formRun(ActiveRun& q, int& numActive) {
+    const float top = fminf(q.rem > 0 ? q.remTop : FLT_MAX, q.head.x);
+    int n = q.rem;
+    q.rem = 0;
+    q.runTop = top;
+    q.front = 0;
+    // stored thresholds with the same top join the remainders, each behind every entry that is not strictly below it
+    while (q.haveHead() && !(q.head.x > top)) {
+        if (n == kActiveCap) { q.bad = true; numActive = 0; return top; }
+        const Thr t{q.head.x, q.head.y, q.head.z, q.head.w};
+        const uint32_t h = q.headH;
+        int j = n;
+        while (j > 0) {
+            const float4 u = q.thr[(j - 1) * 32];
+            const uint32_t uh = q.hdr[(j - 1) * 32];
+            if (!isBelow(uh, Thr{top, u.x, u.y, u.z}, h, t)) break;
+            q.thr[j * 32] = u;
+            q.hdr[j * 32] = uh;
+            j--;
+        }
+        q.thr[j * 32] = make_float4(t.bottom, t.left, t.right, 0.0f);
+        q.hdr[j * 32] = h;
+        n++;
+        q.advance();
+    }
+    // countActive + nextSlicePoint: the next top below the run, the run's smallest bottom
+    float slicePoint = q.head.x;    // FLT_MAX when the store is exhausted
+    for (int i = 0; i < n; i++) {
+        const float bottom = q.thr[i * 32].x;
+        if (top < bottom) slicePoint = fminf(slicePoint, bottom);
+    }
+    q.cutY = slicePoint;
+    // sliceActive: where each threshold that reaches below the slice point crosses it
+    bool nan = false;
+    for (int i = 0; i < n; i++) {
+        const float4 v = q.thr[i * 32];
+        if ((top < slicePoint) && (slicePoint < v.x)) {
+            const float splitX = intersectX(q.hdr[i * 32], Thr{top, v.x, v.y, v.z}, slicePoint);
+            q.thr[i * 32].w = splitX;
+            nan = nan || (splitX != splitX);
+        }
+    }
+    if (nan) { q.bad = true; numActive = 0; return top; }
+    numActive = n;
+    return slicePoint;
+}
+
 // verticalAdvance, K.cl:1744-1824, without the shape stack: what it does to the stack (toggling the persistent
 // thresholds that cross the band border) goes into the stream as FLIP records; the un-toggling of the band that
 // ended (K.cl:1756-1759) is the resolve kernel resetting `cur` at the next first-of-band section.
-template <class Q>
-__device__ __forceinline__ void sliceVertical(const FrameParams& P, SliceScratch& W, StreamWriter& out, Q& q, SweepState& st,
+__device__ __forceinline__ void sliceVertical(const FrameParams& P, SliceScratch& W, StreamWriter& out, ActiveRun& q, SweepState& st,
                                               float floatHeight) {
     st.gapTop = 0.0f;
     const float nextBreak = fminf(floatHeight, st.pixelY);
-    const float activeBottom = q.len > 0 ? q.getT(0).bottom : FLT_MAX;
-    if (activeBottom == st.ey) {   // the active run ends here: its persistent bottoms toggle, then it is popped
+    const float activeBottom = st.numActive > 0 ? q.upperBottom(q.front) : FLT_MAX;
+    if (st.numActive > 0 && activeBottom == st.ey) {   // the active run ends here: its persistent bottoms toggle, then it is popped
         for (int i = 0; i < st.numActive; i++) {
-            const uint32_t h = q.getH(i);
+            const uint32_t h = q.upperHeader(q.front + i);
             if (hPersistBottom(h)) out.put(P, W, kRecFlip | (h & kRecBitMask), 0u);
         }
-        q.popN(st.numActive);
+        runToRemainders(q, st.numActive);
         st.numActive = 0;
     }
     float nextBottom;
     if (st.numActive > 0) {
         nextBottom = fminf(activeBottom, nextBreak);
     } else {
-        const float nextTop = q.len > 0 ? q.getT(0).top : FLT_MAX;
+        const float nextTop = fminf(q.rem > 0 ? q.remTop : FLT_MAX, q.head.x);
         if (nextTop > st.ey) {
             nextBottom = fminf(nextBreak, nextTop);
             st.gapTop = nextTop;   // nothing crosses the column above this y
         } else {
-            float activeTop;
-            nextBottom = fminf(nextBreak, splitNext(q, st.numActive, activeTop));
-            while (st.numActive > 0) {
-                const Thr t0 = q.getT(0);
-                if (t0.top != t0.bottom) break;
-                const uint32_t h = q.getH(0);
+            nextBottom = fminf(nextBreak, formRun(q, st.numActive));
+            while (st.numActive > 0) {   // zero-height thresholds in front of the run: K.cl:1794-1799
+                if (q.runTop != q.upperBottom(q.front)) break;
+                const uint32_t h = q.upperHeader(q.front);
                 if (hPersistTop(h)) out.put(P, W, kRecFlip | (h & kRecBitMask), 0u);
-                q.pop();
+                q.front++;
                 st.numActive--;
             }
             // K.cl:1803-1808 tests tTop(threshold i) > RENDERSTART per active; the actives share their top
-            if (activeTop > 0.0f) {
+            if (q.runTop > 0.0f) {
                 for (int i = 0; i < st.numActive; i++) {
-                    const uint32_t h = q.getH(i);
+                    const uint32_t h = q.upperHeader(q.front + i);
                     if (hPersistTop(h)) out.put(P, W, kRecFlip | (h & kRecBitMask), 0u);
                 }
             }
@@ -155,9 +306,9 @@ __device__ __forceinline__ void sliceVertical(const FrameParams& P, SliceScratch
 
 // ---- slice kernel body -------------------------------------------------------------------------------------------
 // One warp, one (tile, 32-column group) of a dense tile.  Returns per lane 1 if the thread has to be replayed
-// (its queue outgrew the on-chip capacity while slicing, or the stream pool ran out: `exhausted`).
+// (a run outgrew the on-chip capacity, a NaN turned up, or the stream pool ran out: `exhausted`).
 // `rec`: the lane's thread record, null for a lane that has no column-thread in this unit (units narrower than a warp)
-__device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, LaneQueue& q, const gudni_tile& tile,
+__device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, ActiveRun& q, const gudni_tile& tile,
                                          ThreadRec* recp, int column, bool& exhausted) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -172,16 +323,16 @@ __device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, 
     const float floatHeight = (float)g.intHeight;
     SweepState st;
     st.alive = false;
-    q.init();
     ensureSlab(P, W, 32u + kSlabLow);
     StreamWriter out;
     out.failed = false; out.pos = 0; out.first = 0u; out.chunk = P.streamPool;
+    q.attach(P.thrStore, P.hdrStore, recOffset, mine ? (int)recCount : 0);
+    bool spilled = false;
     if (mine) {
-        q.attach(P.thrStore, P.hdrStore, recOffset, (int)recCount, kStoreSlack);
         st.init(floatHeight);
         out.open(P, W);
+        if (recp->pad1 & kRecUnordered) { spilled = true; st.alive = false; }   // a NaN among its thresholds (raster_sort_kernel)
     }
-    bool spilled = false;
     bool first = false;    // the next section record opens a band
     int blankRun = 1;      // pixels the band being swept stands for
     for (;;) {
@@ -203,7 +354,7 @@ __device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, 
             }
             if (st.alive) {
                 sliceVertical(P, W, out, q, st, floatHeight);
-                if (q.failed()) { spilled = true; st.alive = false; }
+                if (q.bad) { spilled = true; st.alive = false; }
                 first = true;
                 blankRun = 1;
                 if (foldable && st.sy == st.pixelY - 1.0f) {
@@ -217,8 +368,9 @@ __device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, 
             float nextX = 1.0f;
             uint32_t bit = kRecNoBit;
             if (st.cur < st.numActive) {
-                const Thr t = q.getT(st.cur);
-                const uint32_t h = q.getH(st.cur);
+                Thr t;
+                uint32_t h;
+                q.upper(q.front + st.cur, t, h);
                 const float yMid = st.sy + ((st.ey - st.sy) * 0.5f);
                 const float x = intersectX(h, t, yMid);
                 nextX = (x >= 1.0f) ? 0.0f : fmaxf(0.0f, x);
