@@ -36,13 +36,6 @@ constexpr int kColorWarpsPerCta = GUDNI_COLOR_WARPS;
 // and raster_spill_kernel replays, lane-privately against an HBM queue, the column-threads that did not fit the
 // on-chip structures.  Round 1 ran renderThresholds as one kernel; split this way each phase has the occupancy
 // and the lane utilisation it can reach (profiles/README.md).
-__device__ __forceinline__ void registerSpill(const FrameParams& P, int tileIndex, int column) {
-    // replayed by raster_spill_kernel against an HBM queue of MAXTHRESHOLDS entries
-    const unsigned long long slot = atomicAdd(&P.counters[kCntSpilled], 1ull);
-    if (slot < (unsigned long long)P.spillCapacity)
-        P.spillList[slot] = ((unsigned long long)tileIndex << 32) | (unsigned long long)column;
-}
-
 // generateThresholds (K.cl:2030-2082), one CTA per tile: blockDim.x = threadsPerTile, thread =
 // column-thread.  Dynamic shared memory: the tile's staged strand headers, then one queue window per warp.
 __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams P, int tileBase, int nTiles) {
@@ -71,7 +64,7 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
     unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkGenerate);
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) S.tileSlot = (int)atomicAdd(workCounter, 1u);
+        if (threadIdx.x == 0) { S.tileSlot = (int)atomicAdd(workCounter, 1u); S.anyPicture = 0; }
         __syncthreads();
         const int tileSlot = S.tileSlot;
         if (tileSlot >= nTiles) break;
@@ -89,7 +82,7 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
             t.failed = false;
             q.init();
             generateTileThresholds(P, S, R, q, t, tile, g);
-            failed = packWarp(P, q, g, t.stack, t.bits(), t.failed, tileIndex, column, generated, exhausted);
+            failed = packWarp(P, q, g, t.stack, t.bits(), t.failed, tileIndex, column, generated, exhausted, S.anyPicture != 0);
         } else {
             // a tile that stopped splitting at the 8-pixel floor with more shapes than stack bits:
             // its threads take the lane-private replay path (bit -> shape table, HBM queue)
@@ -198,7 +191,7 @@ __global__ void __launch_bounds__(kResolveWarpsPerCta * 32) raster_resolve_kerne
     ResolveScratch& W = scratch[threadIdx.x >> 5];
     RefSlab slab{kRefNone, 0u, -1};
     forEachUnit(P, tileBase, nTiles, kCntWorkResolve, [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
-        if (tileHasPictures(P, tile)) return;   // raster_picture_kernel
+        if (unitHasPictures(rec)) return;   // raster_picture_kernel
         const unsigned int count = rec ? rec->count : 0u;
         if (resolveWarp(P, W, slab, tileIndex, rec)) {
             atomicAdd(&P.counters[kCntThresholds], 0ull - (unsigned long long)count);
@@ -234,7 +227,7 @@ __global__ void __launch_bounds__(kAccumulateWarpsPerCta * 32) raster_accumulate
     __shared__ AccumScratch scratch[kAccumulateWarpsPerCta];
     AccumScratch& W = scratch[threadIdx.x >> 5];
     forEachUnit(P, tileBase, nTiles, kCntWorkAccumulate, [&](int, const gudni_tile& tile, ThreadRec* rec, int column) {
-        if (tileHasPictures(P, tile)) return;
+        if (unitHasPictures(rec)) return;
         accumulateWarp(P, W, tile, rec, column);
         __syncwarp();
     });
@@ -245,6 +238,7 @@ __global__ void __launch_bounds__(kColorWarpsPerCta * 32) raster_picture_kernel(
     __shared__ TileTable tables[kColorWarpsPerCta];
     TileTable& T = tables[threadIdx.x >> 5];
     forEachUnit(P, tileBase, nTiles, kCntWorkColor, [&](int, const gudni_tile& tile, ThreadRec* rec, int column) {
+        if (!unitHasPictures(rec)) return;
         __syncwarp();
         bool anyPicture, anyWild;
         buildTileTable(P, T, tile, anyPicture, anyWild);

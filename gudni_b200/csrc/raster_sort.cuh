@@ -192,7 +192,7 @@ __device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, T
     }
     if (sequential) {
         // the slice kernel hands such a thread to the replay, which follows the reference's insertion sequence
-        const_cast<ThreadRec*>(recp)->pad1 = kRecUnordered;
+        recp->pad1 |= kRecUnordered;
         StoreQueue q{P.thrStore + offset, P.hdrStore + offset, (int)ownCount};
         sortQueue(q);
     }

@@ -304,6 +304,14 @@ __device__ __forceinline__ void sliceVertical(const FrameParams& P, SliceScratch
     st.cur = 0;
 }
 
+// replayed by raster_spill_kernel against an HBM queue of MAXTHRESHOLDS entries
+__device__ __forceinline__ void registerSpill(const FrameParams& P, int tileIndex, int column) {
+    const unsigned long long slot = atomicAdd(&P.counters[kCntSpilled], 1ull);
+    if (slot < (unsigned long long)P.spillCapacity)
+        P.spillList[slot] = ((unsigned long long)tileIndex << 32) | (unsigned long long)column;
+}
+
+
 // ---- slice kernel body -------------------------------------------------------------------------------------------
 // One warp, one (tile, 32-column group) of a dense tile.  Returns per lane 1 if the thread has to be replayed
 // (a run outgrew the on-chip capacity, a NaN turned up, or the stream pool ran out: `exhausted`).
@@ -311,14 +319,11 @@ __device__ __forceinline__ void sliceVertical(const FrameParams& P, SliceScratch
 __device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, ActiveRun& q, const gudni_tile& tile,
                                          ThreadRec* recp, int column, bool& exhausted) {
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
     const ThreadGeom g = threadGeom(P, tile, column);
-    // a picture's colour depends on the row, so runs of untouched rows are only folded in tiles without pictures
-    bool anyPicture = false;
-    for (uint32_t i = lane; i < tile.shape_count; i += 32)
-        anyPicture = anyPicture || (tagMeta(__ldg(&P.shapes[tile.shape_start + i].tag)) & kMetaPicture);
-    const bool foldable = !__any_sync(full, anyPicture);
     const unsigned int recOffset = recp ? recp->offset : 0u, recCount = recp ? recp->count : kRecInactive;
+    // a picture's colour depends on the row, so runs of untouched rows are only folded in tiles without pictures
+    // (the generate kernel left the tile's answer in every thread record)
+    const bool foldable = !(recp && (recp->pad1 & kRecTilePictures));
     const bool mine = recCount != kRecInactive;
     const float floatHeight = (float)g.intHeight;
     SweepState st;
@@ -455,13 +460,10 @@ __device__ __forceinline__ void colorLines(uint64_t hi, uint64_t lo, uint32_t& l
     line2 = line1 ^ (((t >> 9) & (uint32_t)(kColorLines - 1)) | 1u);
 }
 
-// does the tile list a picture substance?  (warp-cooperative)
-__device__ __forceinline__ bool tileHasPictures(const FrameParams& P, const gudni_tile& tile) {
-    const int lane = threadIdx.x & 31;
-    bool any = false;
-    for (uint32_t i = lane; i < tile.shape_count; i += 32)
-        any = any || (tagMeta(__ldg(&P.shapes[tile.shape_start + i].tag)) & kMetaPicture);
-    return __any_sync(0xffffffffu, any);
+// does the unit's tile list a picture substance?  The generate kernel left the answer in every thread record of
+// the tile (kRecTilePictures); warp-uniform.
+__device__ __forceinline__ bool unitHasPictures(const ThreadRec* recp) {
+    return __any_sync(0xffffffffu, recp != nullptr && (recp->pad1 & kRecTilePictures) != 0u);
 }
 
 // Warp-uniform state of the resolve kernel's stack numbering.
@@ -689,7 +691,9 @@ __device__ __forceinline__ void storePixels(const FrameParams& P, uint32_t* outp
 // sections for the same rows), and 32 lanes storing 4 bytes each to 32 different rows is 32 partial sectors.  So
 // finished pixels first go into a window of kRowWindow rows x 32 columns in shared memory — every lane only ever
 // touches its own column of it — and a row leaves for memory when every lane has produced it: one 128-byte
-// store per row.  A lane that gets kRowWindow rows ahead of the slowest one waits.
+// store per row.  A lane that gets kRowWindow rows ahead of the slowest one waits.  (Letting every lane run on until
+// its window is full between two flushes measured slower — S5 13.5 -> 14.7 ms: one record per lane per round keeps
+// the lanes of neighbouring columns on the same branch.)
 #ifndef GUDNI_ROW_WINDOW
 #define GUDNI_ROW_WINDOW 16
 #endif

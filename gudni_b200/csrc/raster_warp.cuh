@@ -11,19 +11,10 @@ constexpr int kWarpTableCap = 128;                  // shapes a dense tile may l
 #define GUDNI_QUEUE_CAP 256
 #endif
 constexpr int kQueueCap = GUDNI_QUEUE_CAP;          // thresholds per column-thread before the HBM replay takes over
-#ifndef GUDNI_QUEUE_HOT
-#define GUDNI_QUEUE_HOT 8
-#endif
-constexpr int kQueueHot = GUDNI_QUEUE_HOT;           // head window in shared memory (slice kernel; power of two)
 #ifndef GUDNI_GEN_QUEUE_HOT
 #define GUDNI_GEN_QUEUE_HOT 4
 #endif
 constexpr int kGenQueueHot = GUDNI_GEN_QUEUE_HOT;       // ... (generate kernel)
-#ifndef GUDNI_STORE_SLACK
-#define GUDNI_STORE_SLACK 8
-#endif
-constexpr int kStoreSlack = GUDNI_STORE_SLACK;   // free store entries in front of every queue (see HeadQueue)
-typedef HeadQueue<kQueueCap, kQueueHot> LaneQueue;
 
 // ---- sort + pack -----------------------------------------------------------------------------------
 // The warp packs the threshold queues of its column-threads, in the order they were built, into the frame-wide
@@ -38,7 +29,7 @@ typedef WarpQueue<kQueueCap, kGenQueueHot> GenQueue;
 // `column` is the reference's thread number inside the tile; the thread's record goes to threadRecs[tile * threadsPerTile + column]
 __device__ __forceinline__ int packWarp(const FrameParams& P, GenQueue& q, const ThreadGeom& g, const ShapeStack& stack,
                                         uint32_t bits, bool failed, int tileIndex, int column, int& generated,
-                                        bool& exhausted) {
+                                        bool& exhausted, bool tilePictures) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     bool spilled = false;
@@ -56,9 +47,8 @@ __device__ __forceinline__ int packWarp(const FrameParams& P, GenQueue& q, const
             count = q.len;
         }
     }
-    // each non-empty queue gets kStoreSlack free entries in front of it: the sweep keeps the part of the
-    // queue that is not in shared memory in this slice, and slicing makes a queue grow at its head
-    int reserve = count > 0 ? count + kStoreSlack : 0;
+    // the queues lie end to end: the sort works in place and the slice kernel only reads
+    const int reserve = count;
     int incl = reserve;
     for (int d = 1; d < 32; d <<= 1) {
         const int t = __shfl_up_sync(full, incl, d);
@@ -74,7 +64,7 @@ __device__ __forceinline__ int packWarp(const FrameParams& P, GenQueue& q, const
         spilled = spilled || g.active;
         count = 0;
     }
-    const unsigned int offset = (unsigned int)(base + (unsigned long long)(incl - reserve + kStoreSlack));
+    const unsigned int offset = (unsigned int)(base + (unsigned long long)(incl - reserve));
     for (int i = 0; i < count; i++) {
         const Thr t = q.getT(i);
         P.thrStore[offset + i] = make_float4(t.top, t.bottom, t.left, t.right);
@@ -84,7 +74,7 @@ __device__ __forceinline__ int packWarp(const FrameParams& P, GenQueue& q, const
     rec.hi = stack.hi; rec.lo = stack.lo;
     rec.offset = offset;
     rec.count = (g.active && !spilled) ? (unsigned int)count : kRecInactive;
-    rec.chunk = 0u; rec.pad1 = 0u;
+    rec.chunk = 0u; rec.pad1 = tilePictures ? kRecTilePictures : 0u;
     P.threadRecs[((size_t)tileIndex << P.computeDepth) + (size_t)column] = rec;
     return spilled ? 1 : 0;
 }
@@ -119,6 +109,7 @@ struct TileStage {
     StrandEntry entry[kStrandTableCap];
     uint32_t shapeBase[kWarpTableCap + 1];   // exclusive scan of the strand counts of the tile's shapes
     int tileSlot;                            // the CTA's current tile
+    int anyPicture;                          // ... lists a picture substance
 };
 
 struct GenThread {   // what buildThresholdArray carries through the tile's shape list (K.cl:1540-1595)
@@ -182,6 +173,8 @@ __device__ __forceinline__ void generateTileThresholds(const FrameParams& P, Til
     const uint32_t numShapes = tile.shape_count;   // <= kWarpTableCap here
     // strand counts -> exclusive scan (a handful of shapes per thread of the first warp)
     __syncthreads();
+    for (uint32_t i = (uint32_t)tid; i < numShapes; i += (uint32_t)nThreads)   // (S.anyPicture was cleared with the tile fetch)
+        if (tagMeta(__ldg(&P.shapes[tile.shape_start + i].tag)) & kMetaPicture) S.anyPicture = 1;
     if (tid < 32) {
         uint32_t mine[(kWarpTableCap + 31) / 32];
         uint32_t sum = 0;

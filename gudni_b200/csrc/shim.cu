@@ -70,8 +70,8 @@ int ensureFrameBuffer(gudni_ctx* ctx) {
     return devEnsure(ctx, ctx->frame, std::max<size_t>(bytes, 4));
 }
 
-// Hand-over buffers between the kernels.  Threshold store (generate -> slice): a first guess of 12 thresholds
-// + the 8 slack entries (kStoreSlack) per column-thread or one per four pixels, whichever is more.  Section
+// Hand-over buffers between the kernels.  Threshold store (generate -> sort -> slice): a first guess of 20 thresholds
+// per column-thread or one per four pixels, whichever is more.  Section
 // stream pool (slice -> colour): 6 chunks of 16 records per column-thread + one per 64 pixels.  Both first
 // guesses are capped by a byte budget; afterwards each is sized 25 % above what the previous frame drew.  A frame
 // that runs one of them dry hands the threads that found it empty to the replay kernel and frame_end then
