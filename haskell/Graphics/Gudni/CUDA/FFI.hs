@@ -74,3 +74,41 @@ foreign import ccall safe "gudni_b200_host_unregister"
 -- [rowBegin, rowEnd) of the canvas; call between frame_begin and the raster calls.
 foreign import ccall safe "gudni_b200_frame_strip"
   c_frameStrip :: Ptr GudniCtx -> CInt -> CInt -> IO CInt
+
+-- | gudni_generations (five Word64: geometry, substances, pictures, picture uses, entries).  A generation that is
+-- unchanged since the last frame means "the bytes behind this pointer are the ones already on the device": the upload is
+-- skipped.  0 = always upload.  The caller bumps a counter whenever it refills the Pile (resetPile / addToPile).
+foreign import ccall safe "gudni_b200_frame_begin_cached"
+  c_frameBeginCached :: Ptr GudniCtx
+                     -> Ptr CChar -> CSize -> Ptr CFloat -> CInt -> Ptr Word8 -> CSize -> Ptr () -> CInt
+                     -> Ptr CFloat -> CInt -> CInt -> CInt
+                     -> Ptr Word64               -- gudni_generations
+                     -> IO CInt
+
+foreign import ccall safe "gudni_b200_raster_scene_cached"
+  c_rasterSceneCached :: Ptr GudniCtx -> Ptr () -> CInt -> Word64 -> IO CInt
+
+-- | Several GPUs of one box behind one call (include/gudni_b200.h, gudni_b200_multi_*): the canvas is cut into strips
+-- of whole root-tile rows, one per device, re-cut every frame from the measured times; every device copies its rows
+-- straight into the HostBitmapTarget.
+data GudniMulti
+
+foreign import ccall safe "gudni_b200_multi_init"
+  c_multiInit :: CInt -> Ptr CInt {- devices or nullPtr -} -> Ptr CInt {- want spec or nullPtr -} -> Ptr CInt {- got spec -}
+              -> Ptr (Ptr GudniMulti) -> IO CInt
+
+foreign import ccall safe "gudni_b200_multi_frame"
+  c_multiFrame :: Ptr GudniMulti
+               -> Ptr CChar -> CSize -> Ptr CFloat -> CInt -> Ptr Word8 -> CSize -> Ptr () -> CInt
+               -> Ptr CFloat -> CInt -> CInt -> CInt
+               -> Ptr () -> CInt                 -- un-binned shape entries (32 bytes each)
+               -> Ptr Word64                     -- gudni_generations or nullPtr
+               -> Ptr CUInt                      -- HostBitmapTarget pointer
+               -> Ptr ()                         -- gudni_multi_stats or nullPtr
+               -> IO CInt
+
+foreign import ccall safe "gudni_b200_multi_last_error"
+  c_multiLastError :: Ptr GudniMulti -> IO CString
+
+foreign import ccall safe "gudni_b200_multi_destroy"
+  c_multiDestroy :: Ptr GudniMulti -> IO ()
