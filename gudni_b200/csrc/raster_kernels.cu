@@ -144,8 +144,10 @@ __device__ __forceinline__ void forEachUnit(const FrameParams& P, int tileBase, 
 __global__ void __launch_bounds__(kSortWarpsPerCta * 32) raster_sort_kernel(const FrameParams P, int tileBase, int nTiles) {
     __shared__ SortScratch scratch[kSortWarpsPerCta];
     SortScratch& W = scratch[threadIdx.x >> 5];
+    BulkStage B;
+    bulkInit(W, B);
     forEachUnit(P, tileBase, nTiles, kCntWorkSort, [&](int, const gudni_tile&, ThreadRec* rec, int) {
-        sortWarp(P, W, rec);
+        sortWarp(P, W, B, rec);
         __syncwarp();
     });
 }

@@ -42,10 +42,61 @@ struct SortScratch {
     float4 key[kSortCap];       // (top, x at the top, inverse slope, header bits): what isBelow compares, one 16-byte load
     float4 thr[kSortCap];       // (top, bottom, left, right)
     uint32_t info[kSortCap];    // lane | first staged index of the element's queue << 5 | queue length << 16
+    uint32_t hdrRaw[kSortCap + 8];   // headers as the bulk copy lands them: from the 16-byte boundary below the batch's first
+    unsigned long long mbar;    // transaction barrier the bulk copies complete on
     unsigned int first[33];     // staged index of each lane's first element (exclusive scan of the lengths)
     unsigned int offset[32];    // each lane's place in the store
     unsigned int nanMask;       // lanes whose queue holds a NaN key
 };
+
+// ---- staging by bulk copy ---------------------------------------------------------------------------------------
+// The queues of a unit lie end to end in the store (the generate kernel packs a warp's queues with one prefix sum), so
+// a batch is one contiguous run of float4 thresholds and one of header words: two 1-D bulk copies (TMA,
+// cp.async.bulk global -> shared, completion on an mbarrier) issued by one lane, instead of a gather per element.
+// The header run starts on a 4-byte boundary; the copy starts at the 16-byte boundary below it.
+struct BulkStage {
+    uint32_t phase;   // parity of the barrier's current phase (warp-uniform)
+};
+__device__ __forceinline__ void bulkInit(SortScratch& W, BulkStage& B) {
+    B.phase = 0u;
+#ifndef GUDNI_HOST_EMULATION
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&W.mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
+    __syncwarp();
+}
+// Whole warp.  Afterwards W.thr[0 .. n) and W.hdrRaw[pad .. pad + n) hold store[first .. first + n); returns pad.
+__device__ __forceinline__ unsigned int bulkStage(const FrameParams& P, SortScratch& W, BulkStage& B, unsigned int first, unsigned int n) {
+    const unsigned int first4 = first & ~3u, pad = first - first4;
+    const unsigned int hdrBytes = ((pad + n) * 4u + 15u) & ~15u;
+    __syncwarp();
+#ifdef GUDNI_HOST_EMULATION
+    if ((threadIdx.x & 31) == 0) {
+        for (unsigned int i = 0; i < n; i++) W.thr[i] = P.thrStore[first + i];
+        for (unsigned int i = 0; i < hdrBytes / 4u; i++) W.hdrRaw[i] = P.hdrStore[first4 + i];
+    }
+    __syncwarp();
+#else
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&W.mbar);
+    if ((threadIdx.x & 31) == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n * 16u + hdrBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(W.thr)), "l"(P.thrStore + first), "r"(n * 16u), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(W.hdrRaw)), "l"(P.hdrStore + first4), "r"(hdrBytes), "r"(bar) : "memory");
+    }
+    uint32_t landed = 0u;
+    while (!landed) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(landed) : "r"(bar), "r"(B.phase) : "memory");
+    }
+    B.phase ^= 1u;
+#endif
+    return pad;
+}
 
 // the queue as it lies in the store, for the sequential fallback
 struct StoreQueue {
@@ -63,22 +114,21 @@ __device__ __forceinline__ bool keyBelow(const float4& a, const float4& b) {
 }
 
 // One warp, one long queue (n > kSortLong) at store[offset ...].  Returns false (nothing written) if a key is NaN.
-__device__ __forceinline__ bool sortLongQueue(const FrameParams& P, SortScratch& W, unsigned int offset, unsigned int n) {
+__device__ __forceinline__ bool sortLongQueue(const FrameParams& P, SortScratch& W, BulkStage& B, unsigned int offset, unsigned int n) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     unsigned int size = 128;
     while (size < n) size <<= 1;                 // n <= kQueueCap <= kSortCap
     uint32_t* perm = W.info;
     bool nan = false;
-    __syncwarp();
+    const unsigned int pad = bulkStage(P, W, B, offset, n);
     for (unsigned int f = lane; f < size; f += 32) {
         perm[f] = f;
         if (f < n) {
-            const float4 t = P.thrStore[offset + f];
-            const uint32_t h = P.hdrStore[offset + f];
+            const float4 t = W.thr[f];
+            const uint32_t h = W.hdrRaw[pad + f];
             const Thr th{t.x, t.y, t.z, t.w};
             const float4 k = make_float4(t.x, tTopX(h, th), invSlope(h, th), __uint_as_float(h));
-            W.thr[f] = t;
             W.key[f] = k;
             nan = nan || (t.x != t.x) || (t.y != t.y) || (t.z != t.z) || (t.w != t.w) || (k.z != k.z);
         }
@@ -113,7 +163,7 @@ __device__ __forceinline__ bool sortLongQueue(const FrameParams& P, SortScratch&
 }
 
 // One warp, the queues of one unit.  `recp`: the lane's thread record (null: no column-thread in this lane).
-__device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, ThreadRec* recp) {
+__device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, BulkStage& B, ThreadRec* recp) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     unsigned int count = 0u, offset = 0u;
@@ -127,9 +177,10 @@ __device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, T
     const bool isLong = count > kSortLong;
     for (unsigned longLanes = __ballot_sync(full, isLong); longLanes; longLanes &= longLanes - 1u) {
         const int l = __ffs((int)longLanes) - 1;
-        const bool sorted = sortLongQueue(P, W, __shfl_sync(full, offset, l), __shfl_sync(full, count, l));
+        const bool sorted = sortLongQueue(P, W, B, __shfl_sync(full, offset, l), __shfl_sync(full, count, l));
         if (!sorted && lane == l) sequential = true;
     }
+    const unsigned longMask = __ballot_sync(full, isLong);
     if (isLong) count = 0u;    // (done, or left to the sequential sort below)
     const unsigned int ownCount = isLong ? recp->count : count;
     int laneBegin = 0;
@@ -140,7 +191,9 @@ __device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, T
             const unsigned int v = __shfl_up_sync(full, incl, d);
             if (lane >= d) incl += v;
         }
-        const unsigned fits = __ballot_sync(full, lane >= laneBegin && incl <= (unsigned int)kSortCap) >> laneBegin;
+        // (a long queue lies between its neighbours in the store: a batch, one contiguous run, stops in front of it)
+        const bool longBefore = lane > laneBegin && ((longMask >> laneBegin) & ((2u << (lane - laneBegin)) - 1u)) != 0u;
+        const unsigned fits = __ballot_sync(full, lane >= laneBegin && incl <= (unsigned int)kSortCap && !longBefore) >> laneBegin;
         // lanes laneBegin .. laneEnd-1 (at least one: a single queue always fits)
         const int laneEnd = fits == (full >> laneBegin) ? 32 : laneBegin + __ffs((int)~fits) - 1;
         const bool inBatch = lane >= laneBegin && lane < laneEnd;
@@ -150,7 +203,12 @@ __device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, T
         W.offset[lane] = offset;
         if (lane == 0) { W.first[32] = total; W.nanMask = 0u; }
         __syncwarp();
-        // ---- stage: the batch's thresholds, flattened; coalesced within a queue ------------------------------------
+        // ---- stage: the batch's thresholds are one contiguous run of the store ------------------------------------------
+        // (its first element: the first non-empty queue of the batch)
+        const unsigned nonEmpty = __ballot_sync(full, inBatch && count > 0u);
+        if (nonEmpty == 0u) { laneBegin = laneEnd; continue; }
+        const unsigned int runFirst = __shfl_sync(full, offset, __ffs((int)nonEmpty) - 1);
+        const unsigned int pad = bulkStage(P, W, B, runFirst, total);
         for (unsigned int f = lane; f < total; f += 32) {
             // the queue element f belongs to: the last lane of the batch whose first index is <= f
             int lo = laneBegin, hi = laneEnd - 1;
@@ -159,12 +217,10 @@ __device__ __forceinline__ void sortWarp(const FrameParams& P, SortScratch& W, T
                 if (W.first[mid] <= f) lo = mid; else hi = mid - 1;
             }
             const unsigned int qs = W.first[lo], n = W.first[lo + 1 < laneEnd ? lo + 1 : 32] - qs;
-            const unsigned int src = W.offset[lo] + (f - qs);
-            const float4 t = P.thrStore[src];
-            const uint32_t h = P.hdrStore[src];
+            const float4 t = W.thr[f];
+            const uint32_t h = W.hdrRaw[pad + f];
             const Thr th{t.x, t.y, t.z, t.w};
             const float4 k = make_float4(t.x, tTopX(h, th), invSlope(h, th), __uint_as_float(h));
-            W.thr[f] = t;
             W.key[f] = k;
             W.info[f] = (uint32_t)lo | (qs << 5) | (n << 16);
             // a NaN anywhere in a queue: that queue's lane sorts it sequentially (the order then depends on the comparison sequence)

@@ -84,8 +84,8 @@ int ensureHandover(gudni_ctx* ctx, int64_t totalTiles) {
     const size_t guess = std::min(std::max(threads * 20, pixels / 4), kFirstGuessBudget / 20);
     const size_t entries = std::max({guess, (size_t)(ctx->storeDemand + ctx->storeDemand / 4), (size_t)1 << 20});
     GUDNI_TRY(devEnsure(ctx, ctx->thrStore, entries * 16));
-    GUDNI_TRY(devEnsure(ctx, ctx->hdrStore, entries * 4));
-    ctx->storeCap = std::min(ctx->thrStore.cap / 16, ctx->hdrStore.cap / 4);
+    GUDNI_TRY(devEnsure(ctx, ctx->hdrStore, entries * 4 + 64));   // (+64: the sort kernel's bulk copies of header words are rounded out to 16 bytes)
+    ctx->storeCap = std::min(ctx->thrStore.cap / 16, (ctx->hdrStore.cap - 64) / 4);
     const size_t chunkGuess = std::min(threads * 6 + pixels / 64, kFirstGuessBudget / 128);
     const size_t chunks = std::max({chunkGuess, (size_t)(ctx->streamDemand + ctx->streamDemand / 4), (size_t)1 << 14});
     GUDNI_TRY(devEnsure(ctx, ctx->streamPool, chunks * 128));

@@ -117,7 +117,7 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
     const size_t entries = g_storeEntriesOverride ? g_storeEntriesOverride
                                                   : std::max<size_t>({threads * 24, (size_t)in.width * in.height / 4, (size_t)1 << 16});
     std::vector<float4> thrStore(entries);
-    std::vector<uint32_t> hdrStore(entries);
+    std::vector<uint32_t> hdrStore(entries + 16);   // (+16 words: bulk copies of headers are rounded out to 16 bytes)
     std::vector<ThreadRec> recs(std::max<size_t>(threads, 32));
     std::vector<uint32_t> order(std::max(nTiles, 1));
     std::vector<float2> bounds(in.geometryBytes / 16 + 2);
