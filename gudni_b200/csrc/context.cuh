@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/gudni_b200.h"
 
@@ -75,6 +76,12 @@ struct gudni_ctx {
     unsigned long long refCapSlabs = 0;
     unsigned long long refDemand = 0;          // slabs of stack numbers drawn last frame
     int spillSlots = 0;
+    // a launch's tiles go through the kernels in `batches` interleaved batches, each on its own stream (rasterTiles)
+    int batches = 1;
+    bool batchOrdered = false;   // batches are runs of the cost order (the first one the most expensive tiles) instead of interleaved
+    std::vector<cudaStream_t> batchStreams;   // batches beyond the first
+    std::vector<cudaEvent_t> evJoin;
+    cudaEvent_t evFork = nullptr;
     int64_t uploadsSkipped = 0;           // input-cache hits (gudni_b200_frame_begin_cached)
     int64_t retriedFrames = 0;            // frames rasterized twice because a per-frame buffer was undersized
 

@@ -61,14 +61,14 @@ __global__ void __launch_bounds__(1024) raster_generate_kernel(const FrameParams
     q.thrHot = scratch[warp].qThr + lane;
     q.hdrHot = scratch[warp].qHdr + lane;
     const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
-    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkGenerate);
+    unsigned int* workCounter = P.work + kWorkGenerate;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) { S.tileSlot = (int)atomicAdd(workCounter, 1u); S.anyPicture = 0; }
         __syncthreads();
         const int tileSlot = S.tileSlot;
         if (tileSlot >= nTiles) break;
-        const int tileIndex = (int)P.tileOrder[tileBase + tileSlot];
+        const int tileIndex = (int)P.tileOrder[tileBase + tileSlot * P.batchStride + P.batchIndex];
         const gudni_tile tile = P.tiles[tileIndex];
         const int column = (int)threadIdx.x;   // the reference's thread number inside the tile
         const ThreadGeom g = threadGeom(P, tile, column);
@@ -125,13 +125,13 @@ __device__ __forceinline__ void forEachUnit(const FrameParams& P, int tileBase, 
     const int lanesPerUnit = 32 >> P.laneShift;
     const unsigned totalUnits = (unsigned)nTiles << unitShift;
     const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
-    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + counterSlot);
+    unsigned int* workCounter = P.work + counterSlot;
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd(workCounter, 1u);
         unit = __shfl_sync(full, unit, 0);
         if (unit >= totalUnits) break;
-        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> unitShift)];
+        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> unitShift) * P.batchStride + P.batchIndex];
         const unsigned unitInTile = unit & ((1u << unitShift) - 1u);
         const gudni_tile tile = P.tiles[tileIndex];
         if (tile.shape_count > denseCap) continue;   // replayed lane-privately
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kSortWarpsPerCta * 32) raster_sort_kernel(cons
     SortScratch& W = scratch[threadIdx.x >> 5];
     BulkStage B;
     bulkInit(W, B);
-    forEachUnit(P, tileBase, nTiles, kCntWorkSort, [&](int, const gudni_tile&, ThreadRec* rec, int) {
+    forEachUnit(P, tileBase, nTiles, kWorkSort, [&](int, const gudni_tile&, ThreadRec* rec, int) {
         sortWarp(P, W, B, rec);
         __syncwarp();
     });
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kSliceWarpsPerCta * 32, GUDNI_SLICE_MIN_CTAS) 
     ActiveRun q;
     q.thr = W.aThr + lane;
     q.hdr = W.aHdr + lane;
-    forEachUnit(P, tileBase, nTiles, kCntWorkSweep, [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
+    forEachUnit(P, tileBase, nTiles, kWorkSlice, [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
         const unsigned int count = rec ? rec->count : 0u;
         bool exhausted = false;
         const int failed = sliceWarp(P, W, q, tile, rec, column, exhausted);
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kResolveWarpsPerCta * 32) raster_resolve_kerne
     __shared__ ResolveScratch scratch[kResolveWarpsPerCta];
     ResolveScratch& W = scratch[threadIdx.x >> 5];
     RefSlab slab{kRefNone, 0u, -1};
-    forEachUnit(P, tileBase, nTiles, kCntWorkResolve, [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
+    forEachUnit(P, tileBase, nTiles, kWorkResolve, [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
         if (unitHasPictures(rec)) return;   // raster_picture_kernel
         const unsigned int count = rec ? rec->count : 0u;
         if (resolveWarp(P, W, slab, tileIndex, rec)) {
@@ -210,17 +210,21 @@ __global__ void __launch_bounds__(kCompositeWarpsPerCta * 32) raster_composite_k
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     TileTable& T = tables[threadIdx.x >> 5];
-    const unsigned int nSlabs = (unsigned int)min(P.counters[kCntRefSlabs], (unsigned long long)P.refCapSlabs);
-    const unsigned int firstSlab = (unsigned int)P.counters[kCntCompositeBase];
-    unsigned int* workCounter = reinterpret_cast<unsigned int*>(P.counters + kCntWorkComposite);
+    // the slabs the batch's resolve pass filled: its region of the table, from the start (the table is reused launch by launch)
+    const unsigned int drawn = P.work[kWorkRefSlabs];
+    const unsigned int nSlabs = min(drawn, P.refCapSlabs);
+    // what the whole table would have to hold for this launch: every batch as much as the hungriest one
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicMax(&P.counters[kCntRefSlabs], (unsigned long long)drawn * (unsigned long long)P.batchCount);
+    unsigned int* workCounter = P.work + kWorkComposite;
     int tableTile = -1;
     bool tame = false;
     for (;;) {
         unsigned int s = 0;
-        if (lane == 0) s = firstSlab + atomicAdd(workCounter, 1u);
+        if (lane == 0) s = atomicAdd(workCounter, 1u);
         s = __shfl_sync(full, s, 0);
         if (s >= nSlabs) break;
-        compositeSlab(P, T, tableTile, tame, s);
+        compositeSlab(P, T, tableTile, tame, P.refSlabBase + s);
     }
 }
 
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(kCompositeWarpsPerCta * 32) raster_composite_k
 __global__ void __launch_bounds__(kAccumulateWarpsPerCta * 32) raster_accumulate_kernel(const FrameParams P, int tileBase, int nTiles) {
     __shared__ AccumScratch scratch[kAccumulateWarpsPerCta];
     AccumScratch& W = scratch[threadIdx.x >> 5];
-    forEachUnit(P, tileBase, nTiles, kCntWorkAccumulate, [&](int, const gudni_tile& tile, ThreadRec* rec, int column) {
+    forEachUnit(P, tileBase, nTiles, kWorkAccumulate, [&](int, const gudni_tile& tile, ThreadRec* rec, int column) {
         if (unitHasPictures(rec)) return;
         accumulateWarp(P, W, tile, rec, column);
         __syncwarp();
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(kAccumulateWarpsPerCta * 32) raster_accumulate
 __global__ void __launch_bounds__(kColorWarpsPerCta * 32) raster_picture_kernel(const FrameParams P, int tileBase, int nTiles) {
     __shared__ TileTable tables[kColorWarpsPerCta];
     TileTable& T = tables[threadIdx.x >> 5];
-    forEachUnit(P, tileBase, nTiles, kCntWorkColor, [&](int, const gudni_tile& tile, ThreadRec* rec, int column) {
+    forEachUnit(P, tileBase, nTiles, kWorkPicture, [&](int, const gudni_tile& tile, ThreadRec* rec, int column) {
         if (!unitHasPictures(rec)) return;
         __syncwarp();
         bool anyPicture, anyWild;
@@ -283,8 +287,6 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(gudni_tile* __restrict
                                                           uint32_t* __restrict__ order, unsigned long long* __restrict__ counters) {
     __shared__ unsigned int bins[256];
     __shared__ unsigned int starts[256];
-    // the stack table runs on across the launches of a frame: this launch's composite pass starts where the table stands now
-    if (threadIdx.x == 0) counters[kCntCompositeBase] = counters[kCntRefSlabs];
     if (counters[kCntNonFinite])
         for (int i = threadIdx.x; i < nTiles; i += blockDim.x) tiles[tileBase + i].shape_count = 0u;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) bins[i] = 0u;
@@ -383,6 +385,22 @@ int selftestDiv3(gudni_ctx* ctx, unsigned long long n, unsigned long long seed, 
     return GUDNI_OK;
 }
 
+// streams and events of the batches beyond the first (which runs on the context's own stream)
+static int ensureBatchStreams(gudni_ctx* ctx, int batches) {
+    while ((int)ctx->batchStreams.size() < batches - 1) {
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+        int lowest = 0, highest = 0;   // the first batch (the context's own stream) keeps the default priority: it is the critical one
+        GUDNI_CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lowest, &highest));
+        GUDNI_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, lowest));
+        ctx->batchStreams.push_back(st);
+        GUDNI_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->evJoin.push_back(ev);
+    }
+    if (batches > 1 && !ctx->evFork) GUDNI_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+    return GUDNI_OK;
+}
+
 int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTiles) {
     if (nTiles <= 0) return GUDNI_OK;
     FrameParams P = frame;
@@ -421,34 +439,57 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
         ctx->occupancyKnown = true;
     }
     const int numSms = ctx->numSms;
-    P.numStreams = std::max(1, std::min(std::min(numSms, gudni_dev::kMaxSms), nTiles));
-    // work counters of the kernels (the threshold store and stream cursors run on across the jobs of a frame)
-    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 32, 0, gudni_dev::kMaxSms * sizeof(unsigned int), ctx->stream));
-    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkSweep, 0, 8, ctx->stream));
-    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkGenerate, 0, 8, ctx->stream));
-    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkColor, 0, 8, ctx->stream));
-    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkResolve, 0, 24, ctx->stream));
-    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.as<unsigned long long>() + gudni_dev::kCntWorkSort, 0, 8, ctx->stream));
-    // units narrower than a warp when whole-warp units would not go round (see forEachUnit)
-    long long units = (long long)nTiles * (ctx->spec.threads_per_tile / 32);
-    P.laneShift = 0;
-    while (P.laneShift < GUDNI_MAX_LANE_SHIFT && units < 4ll * numSms * ctx->sliceCtasPerSm * kSliceWarpsPerCta) { P.laneShift++; units *= 2; }
-    auto grid = [&](int ctasPerSm, int warpsPerCta) {
-        return (int)std::min<long long>((long long)ctasPerSm * numSms, (units + warpsPerCta - 1) / warpsPerCta);
-    };
+    // Batches (FrameParams::work).  One batch per ~kBatchTiles tiles, at most kMaxBatches, or what GUDNI_BATCHES says.
+    int batches = ctx->batches > 0 ? ctx->batches : 1;
+    batches = std::max(1, std::min({batches, gudni_dev::kMaxBatches, nTiles}));
+    GUDNI_TRY(ensureBatchStreams(ctx, batches));
+    // work cursors of the kernels (the threshold store and stream cursors run on across the launches of a frame)
+    unsigned int* work = reinterpret_cast<unsigned int*>(ctx->counters.as<unsigned long long>() + 32);
+    GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(work, 0, (size_t)gudni_dev::kMaxBatches * gudni_dev::kWorkWords * sizeof(unsigned int), ctx->stream));
     tile_order_kernel<<<1, 1024, 0, ctx->stream>>>(const_cast<gudni_tile*>(P.tiles), tileBase, nTiles, const_cast<uint32_t*>(P.tileOrder), P.counters);
     ctx->launches++;
-    raster_generate_kernel<<<std::min(ctx->genCtasPerSm * numSms, nTiles), ctx->spec.threads_per_tile, genSmem, ctx->stream>>>(P, tileBase, nTiles);
-    ctx->launches++;
-    raster_sort_kernel<<<grid(ctx->sortCtasPerSm, kSortWarpsPerCta), kSortWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
-    ctx->launches++;
-    raster_slice_kernel<<<grid(ctx->sliceCtasPerSm, kSliceWarpsPerCta), kSliceWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
-    raster_resolve_kernel<<<grid(ctx->resolveCtasPerSm, kResolveWarpsPerCta), kResolveWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
-    raster_composite_kernel<<<ctx->compositeCtasPerSm * numSms, kCompositeWarpsPerCta * 32, 0, ctx->stream>>>(P);
-    raster_accumulate_kernel<<<grid(ctx->accumulateCtasPerSm, kAccumulateWarpsPerCta), kAccumulateWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
-    raster_picture_kernel<<<grid(ctx->colorCtasPerSm, kColorWarpsPerCta), kColorWarpsPerCta * 32, 0, ctx->stream>>>(P, tileBase, nTiles);
-    ctx->launches += 5;
-    GUDNI_CUDA_TRY(ctx, cudaGetLastError());
+    if (batches > 1) GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+    const unsigned int regionSlabs = P.refCapSlabs / (unsigned int)batches;
+    for (int b = 0; b < batches; b++) {
+        cudaStream_t st = b == 0 ? ctx->stream : ctx->batchStreams[b - 1];
+        if (b > 0) GUDNI_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->evFork, 0));
+        // interleaved: places b, b + B, ... of the launch's cost order; ordered: the b-th run of it (batch 0 the most expensive tiles)
+        int tilesHere = (nTiles - b + batches - 1) / batches;
+        int firstTile = tileBase;
+        P.work = work + (size_t)b * gudni_dev::kWorkWords;
+        P.batchCount = batches;
+        P.batchStride = batches;
+        P.batchIndex = b;
+        if (ctx->batchOrdered) {
+            const int lo = (int)((long long)nTiles * b / batches), hi = (int)((long long)nTiles * (b + 1) / batches);
+            firstTile = tileBase + lo;
+            tilesHere = hi - lo;
+            P.batchStride = 1;
+            P.batchIndex = 0;
+        }
+        P.refSlabBase = (unsigned int)b * regionSlabs;
+        P.refCapSlabs = regionSlabs;
+        // units narrower than a warp when whole-warp units would not go round (see forEachUnit)
+        long long units = (long long)tilesHere * (ctx->spec.threads_per_tile / 32);
+        P.laneShift = 0;
+        while (P.laneShift < GUDNI_MAX_LANE_SHIFT && units < 4ll * numSms * ctx->sliceCtasPerSm * kSliceWarpsPerCta) { P.laneShift++; units *= 2; }
+        auto grid = [&](int ctasPerSm, int warpsPerCta) {
+            return (int)std::min<long long>((long long)ctasPerSm * numSms, (units + warpsPerCta - 1) / warpsPerCta);
+        };
+        raster_generate_kernel<<<std::min(ctx->genCtasPerSm * numSms, tilesHere), ctx->spec.threads_per_tile, genSmem, st>>>(P, firstTile, tilesHere);
+        raster_sort_kernel<<<grid(ctx->sortCtasPerSm, kSortWarpsPerCta), kSortWarpsPerCta * 32, 0, st>>>(P, firstTile, tilesHere);
+        raster_slice_kernel<<<grid(ctx->sliceCtasPerSm, kSliceWarpsPerCta), kSliceWarpsPerCta * 32, 0, st>>>(P, firstTile, tilesHere);
+        raster_resolve_kernel<<<grid(ctx->resolveCtasPerSm, kResolveWarpsPerCta), kResolveWarpsPerCta * 32, 0, st>>>(P, firstTile, tilesHere);
+        raster_composite_kernel<<<ctx->compositeCtasPerSm * numSms, kCompositeWarpsPerCta * 32, 0, st>>>(P);
+        raster_accumulate_kernel<<<grid(ctx->accumulateCtasPerSm, kAccumulateWarpsPerCta), kAccumulateWarpsPerCta * 32, 0, st>>>(P, firstTile, tilesHere);
+        raster_picture_kernel<<<grid(ctx->colorCtasPerSm, kColorWarpsPerCta), kColorWarpsPerCta * 32, 0, st>>>(P, firstTile, tilesHere);
+        ctx->launches += 7;
+        GUDNI_CUDA_TRY(ctx, cudaGetLastError());
+        if (b > 0) {
+            GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evJoin[b - 1], st));
+            GUDNI_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin[b - 1], 0));
+        }
+    }
     return GUDNI_OK;
 }
 

@@ -542,14 +542,14 @@ __device__ __forceinline__ int resolveWarp(const FrameParams& P, ResolveScratch&
             if (slab.base == kRefNone || slab.used + n > kRefSlab) {
                 closeSlab(P, slab);
                 unsigned int s = 0;
-                if (lane == 0) s = (unsigned int)atomicAdd(&P.counters[kCntRefSlabs], 1ull);
+                if (lane == 0) s = atomicAdd(P.work + kWorkRefSlabs, 1u);
                 s = __shfl_sync(full, s, 0);
-                if (s >= P.refCapSlabs) {   // table full: the warp's remaining threads go to the replay
+                if (s >= P.refCapSlabs) {   // the batch's region of the table is full: the warp's remaining threads go to the replay
                     failed = failed || !done;
                     done = true;
                     continue;
                 }
-                slab.base = s * kRefSlab;
+                slab.base = (P.refSlabBase + s) * kRefSlab;
             }
             if (winner) {
                 ref = slab.base + slab.used + (unsigned int)__popc(winners & ((1u << lane) - 1u));
@@ -604,6 +604,12 @@ __device__ __forceinline__ void buildTileTable(const FrameParams& P, TileTable& 
     anyWild = __any_sync(0xffffffffu, wild);
 }
 
+// The tame walk is the composite kernel's inner loop (15.7 M stacks of ~38 layers per S4 frame, 95 % issue-active), so it
+// is written without branches inside a layer: the four words of the stack are walked by four copies of one loop, a layer
+// that does not blend (same substance as the one above, or not an add / continue tag) computes and discards, and
+// composite's `alphaOut > 0` test (K.cl:883) becomes a divisor of 1 — alphaOut is 0 only when the colour so far and the
+// layer both have alpha 0, and then every numerator is exactly 0, so the quotients are the 0 the reference returns.
+#ifdef GUDNI_TAME_BRANCHY
 __device__ __forceinline__ float4 stackColorTame(const TileTable& T, uint64_t hi, uint64_t lo, float4 bgPremul) {
     float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t lastId = 0xFFFFFFFFu;
@@ -627,6 +633,70 @@ __device__ __forceinline__ float4 stackColorTame(const TileTable& T, uint64_t hi
         lastId = id;
     }
 }
+#else
+__device__ __forceinline__ void tameLayer(float& bx, float& by, float& bz, float& bw, const float4 pm, bool take) {
+    const float oneMinus = 1.0f - bw;
+    const float alphaOut = bw + pm.w * oneMinus;
+    const float d = alphaOut > 0.0f ? alphaOut : 1.0f;
+    float qx, qy, qz;
+    div3<false>((bx * bw) + (pm.x * oneMinus), (by * bw) + (pm.y * oneMinus), (bz * bw) + (pm.z * oneMinus), d, qx, qy, qz);
+    bx = take ? qx : bx;
+    by = take ? qy : by;
+    bz = take ? qz : bz;
+    bw = take ? alphaOut : bw;
+}
+#ifdef GUDNI_TAME_UNROLLED
+__device__ __forceinline__ float4 stackColorTame(const TileTable& T, uint64_t hi, uint64_t lo, float4 bgPremul) {
+    float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f;
+    uint32_t lastId = 0xFFFFFFFFu;
+#pragma unroll
+    for (int w = 3; w >= 0; w--) {
+        uint32_t word = (w == 3) ? (uint32_t)(hi >> 32) : (w == 2) ? (uint32_t)hi : (w == 1) ? (uint32_t)(lo >> 32) : (uint32_t)lo;
+        const uint32_t* meta = T.meta + 32 * w;
+        const float4* premul = T.premul + 32 * w;
+        while (word != 0u) {
+            const int b = 31 - __clz((int)word);
+            word ^= (1u << b);
+            const uint32_t m = meta[b];
+            const uint32_t id = m & kMetaIdMask;
+            const bool take = id != lastId && (m & kMetaSet) != 0u;
+            lastId = id;
+            tameLayer(bx, by, bz, bw, premul[b], take);
+            if (bw == 1.0f) return make_float4(bx, by, bz, bw);   // (only a layer that was taken can have made it 1)
+        }
+    }
+    tameLayer(bx, by, bz, bw, bgPremul, true);
+    return make_float4(bx, by, bz, bw);
+}
+#else
+__device__ __forceinline__ float4 stackColorTame(const TileTable& T, uint64_t hi, uint64_t lo, float4 bgPremul) {
+    float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f;
+    uint32_t lastId = 0xFFFFFFFFu;
+    uint32_t word = (uint32_t)(hi >> 32);
+    int wordBase = 96;
+    // one loop for all four words: the lanes of a warp hold different stacks and stay together as long as any has a layer left
+    for (;;) {
+        while (word == 0u) {
+            if (wordBase == 0) {
+                tameLayer(bx, by, bz, bw, bgPremul, true);
+                return make_float4(bx, by, bz, bw);
+            }
+            wordBase -= 32;
+            word = (wordBase == 64) ? (uint32_t)hi : (wordBase == 32) ? (uint32_t)(lo >> 32) : (uint32_t)lo;
+        }
+        const int b = 31 - __clz((int)word);
+        word ^= (1u << b);
+        const int bit = wordBase + b;
+        const uint32_t m = T.meta[bit];
+        const uint32_t id = m & kMetaIdMask;
+        const bool take = id != lastId && (m & kMetaSet) != 0u;
+        lastId = id;
+        tameLayer(bx, by, bz, bw, T.premul[bit], take);
+        if (bw == 1.0f) return make_float4(bx, by, bz, bw);   // (only a layer that was taken can have made it 1)
+    }
+}
+#endif
+#endif
 __device__ __forceinline__ float4 stackColorAny(const FrameParams& P, const TileTable& T, uint64_t hi, uint64_t lo, float4 bgPremul,
                                                 int absX, int absY) {
     float4 base = make_float4(0.f, 0.f, 0.f, 0.f);

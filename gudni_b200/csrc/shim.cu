@@ -77,6 +77,7 @@ int ensureFrameBuffer(gudni_ctx* ctx) {
 // that runs one of them dry hands the threads that found it empty to the replay kernel and frame_end then
 // rasterizes the frame again with the measured demand (see retryExhausted), so an undersized guess costs time on
 // the first frame, never pixels.  One 32-byte record per thread.
+constexpr int kDefaultBatches = 1;
 constexpr size_t kFirstGuessBudget = (size_t)6 << 30;
 int ensureHandover(gudni_ctx* ctx, int64_t totalTiles) {
     const size_t threads = (size_t)totalTiles * (size_t)ctx->spec.threads_per_tile;
@@ -193,6 +194,10 @@ int gudni_b200_init(int device, const gudni_spec* want, gudni_spec* got, gudni_c
         if (cudaEventCreate(e) != cudaSuccess) return fail(GUDNI_ERR_CUDA);
     if (gudni_launch::strandTableInit(ctx) != GUDNI_OK) return fail(GUDNI_ERR_CUDA);
     if (devEnsure(ctx, ctx->counters, gudni_dev::kCountersBytes) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
+    // batches per raster launch (rasterTiles): GUDNI_BATCHES overrides the default
+    ctx->batches = kDefaultBatches;
+    if (const char* e = std::getenv("GUDNI_BATCHES")) ctx->batches = std::max(1, std::min(atoi(e), gudni_dev::kMaxBatches));
+    if (const char* e = std::getenv("GUDNI_BATCH_ORDERED")) ctx->batchOrdered = atoi(e) != 0;
     ctx->spillCapacity = kSpillListCapacity;
     if (devEnsure(ctx, ctx->spillList, (size_t)kSpillListCapacity * 8) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
     ctx->spillSlots = kSpillSlots;
@@ -220,6 +225,9 @@ void gudni_b200_destroy(gudni_ctx* ctx) {
                          ctx->evFirstKernel, ctx->evStrandsDone};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : ctx->batchStreams) cudaStreamDestroy(st);
+    for (cudaEvent_t e : ctx->evJoin) cudaEventDestroy(e);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     delete ctx;

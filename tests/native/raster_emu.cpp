@@ -94,6 +94,7 @@ static size_t g_storeEntriesOverride;
 static size_t g_streamChunksOverride;
 static size_t g_refSlabsOverride;
 static int g_laneShift;
+static int g_batches = 1;
 static int g_rowBegin = 0, g_rowEnd = 0;    // raster_emu_set_strip: rows of the canvas this "context" renders (0,0 = all)
 namespace {
 
@@ -151,7 +152,6 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
     P.threadRecs = recs.data();
     P.strandBounds = bounds.data();
     P.tileOrder = order.data();
-    P.numStreams = std::max(1, std::min(3, nTiles));
     P.laneShift = g_laneShift;
     // section-stream pool (raster_split.cuh): generous (the shim sizes it from the last frame's demand and retries a frame that ran dry), or what raster_emu_set_stream_chunks forces
     const size_t chunks = g_streamChunksOverride ? g_streamChunksOverride
@@ -174,13 +174,26 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
             cuemu::launch(strand_bounds_kernel, dim3((unsigned)((nBoundsRecords + 255) / 256)), dim3(256), P.geometry, in.geometryBytes,
                           static_cast<const uint8_t*>(boundsRecords), boundsStride, (int)nBoundsRecords, bounds.data(), counters.data());
         cuemu::launch(tile_order_kernel, dim3(1), dim3(256), tilesCopy.data(), 0, nTiles, order.data(), counters.data());
-        cuemu::launch(raster_generate_kernel, dim3(2), dim3(in.spec->threads_per_tile), P, 0, nTiles);
-        cuemu::launch(raster_sort_kernel, dim3(2), dim3(kSortWarpsPerCta * 32), P, 0, nTiles);
-        cuemu::launch(raster_slice_kernel, dim3(2), dim3(kSliceWarpsPerCta * 32), P, 0, nTiles);
-        cuemu::launch(raster_resolve_kernel, dim3(2), dim3(kResolveWarpsPerCta * 32), P, 0, nTiles);
-        cuemu::launch(raster_composite_kernel, dim3(2), dim3(kCompositeWarpsPerCta * 32), P);
-        cuemu::launch(raster_accumulate_kernel, dim3(2), dim3(kAccumulateWarpsPerCta * 32), P, 0, nTiles);
-        cuemu::launch(raster_picture_kernel, dim3(2), dim3(kColorWarpsPerCta * 32), P, 0, nTiles);
+        // the batches of rasterTiles (one stream each on the GPU), here one after the other
+        const int batches = std::max(1, std::min({g_batches, kMaxBatches, nTiles}));
+        const unsigned int regionSlabs = (unsigned int)refSlabs / (unsigned int)batches;
+        unsigned int* work = reinterpret_cast<unsigned int*>(counters.data() + 32);
+        for (int b = 0; b < batches; b++) {
+            const int tilesHere = (nTiles - b + batches - 1) / batches;
+            P.work = work + (size_t)b * kWorkWords;
+            P.batchStride = batches;
+            P.batchCount = batches;
+            P.batchIndex = b;
+            P.refSlabBase = (unsigned int)b * regionSlabs;
+            P.refCapSlabs = regionSlabs;
+            cuemu::launch(raster_generate_kernel, dim3(2), dim3(in.spec->threads_per_tile), P, 0, tilesHere);
+            cuemu::launch(raster_sort_kernel, dim3(2), dim3(kSortWarpsPerCta * 32), P, 0, tilesHere);
+            cuemu::launch(raster_slice_kernel, dim3(2), dim3(kSliceWarpsPerCta * 32), P, 0, tilesHere);
+            cuemu::launch(raster_resolve_kernel, dim3(2), dim3(kResolveWarpsPerCta * 32), P, 0, tilesHere);
+            cuemu::launch(raster_composite_kernel, dim3(2), dim3(kCompositeWarpsPerCta * 32), P);
+            cuemu::launch(raster_accumulate_kernel, dim3(2), dim3(kAccumulateWarpsPerCta * 32), P, 0, tilesHere);
+            cuemu::launch(raster_picture_kernel, dim3(2), dim3(kColorWarpsPerCta * 32), P, 0, tilesHere);
+        }
         cuemu::launch(raster_spill_kernel, dim3(1), dim3(spillSlots), P, spillThr.data(), spillHdr.data(), spillSlots);
     }
     (void)nShapes;
@@ -275,6 +288,8 @@ void raster_emu_set_stream_chunks(size_t n) { g_streamChunksOverride = n; }
 void raster_emu_set_ref_slabs(size_t n) { g_refSlabsOverride = n; }
 // the render kernels' units are 32 >> shift column-threads wide (what the shim picks for launches of few tiles)
 void raster_emu_set_lane_shift(int shift) { g_laneShift = shift; }
+// batches per launch (rasterTiles of raster_kernels.cu): emulated one after the other
+void raster_emu_set_batches(int n) { g_batches = n < 1 ? 1 : n; }
 
 // order in which the emulator runs the threads of a CTA between rendezvous points (see runBlock)
 void raster_emu_set_schedule(int mode) { cuemu::scheduleMode = mode; }

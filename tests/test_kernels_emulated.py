@@ -424,6 +424,19 @@ def test_units_narrower_than_a_warp(emu, shift):
         emu.raster_emu_set_lane_shift(0)
 
 
+@pytest.mark.parametrize("batches", [2, 3, 8])
+def test_batches_of_a_launch(emu, batches):
+    """A launch's tiles dealt into interleaved batches with their own work cursors and their own region of the
+    stack table (rasterTiles): same bits; more batches than tiles included."""
+    emu.raster_emu_set_batches(batches)
+    try:
+        run(emu, scenes.fuzzy_circles(150, 200, 150, 4, 40, 6))
+        run(emu, scenes.picture_scene(320, 300, flowers_size=(350, 200)))
+        run(emu, scenes.fuzzy_circles(400, 600, 300, 4, 40, 7), RasterSpec(64, 64, 256, 1024, 1022, 127))
+    finally:
+        emu.raster_emu_set_batches(1)
+
+
 def test_device_derived_spec(emu, emu_scene):
     """The RasterSpec the reference would derive from the B200's OpenCL device (1,024-pixel tiles, 1,024 threads
     per tile, MAXTHRESHOLDS 2,853 — tests/test_reference_pin.py): 32 warps per tile, 1,024-pixel root tiles."""
