@@ -62,6 +62,7 @@ struct gudni_ctx {
     DevBuf spillThr, spillHdr;
     DevBuf thrStore, hdrStore, threadRecs;   // generate -> sweep hand-over
     DevBuf tileOrder;                        // tiles of a launch by decreasing shape count
+    DevBuf wideList;                         // units with a thread for raster_slice_wide_kernel (one region per batch of a launch)
     DevBuf strandBounds;                     // per-strand y range, geometry_bytes / 16 entries
     unsigned long long storeCap = 0;
     unsigned long long storeDemand = 0;   // thresholds the generate kernel wanted to store last frame
@@ -110,7 +111,9 @@ struct gudni_ctx {
 
     // timing
     cudaEvent_t evFrameBegin = nullptr, evUploadDone = nullptr, evBinDone = nullptr, evRasterDone = nullptr,
-                evDownloadDone = nullptr, evFirstKernel = nullptr, evStrandsDone = nullptr;
+                evDownloadDone = nullptr, evFirstKernel = nullptr, evStrandsDone = nullptr, evGeometryUp = nullptr;
+    bool geometryPending = false;   // the geometry heap is still crossing PCIe on the copy stream (waitGeometry, shim.cu)
+    bool geometryTimed = false;     // ... this frame uploaded it there
     bool firstKernelRecorded = false;
     float lastFrameMs = 0.f;
     gudni_stats lastStats{};

@@ -174,15 +174,60 @@ __global__ void __launch_bounds__(kSliceWarpsPerCta * 32, GUDNI_SLICE_MIN_CTAS) 
     q.hdr = W.aHdr + lane;
     forEachUnit(P, tileBase, nTiles, kWorkSlice, [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
         const unsigned int count = rec ? rec->count : 0u;
-        bool exhausted = false;
-        const int failed = sliceWarp(P, W, q, tile, rec, column, exhausted);
+        bool exhausted = false, wide = false;
+        const int failed = sliceWarp<kActiveCap>(P, W, q, tile, rec, column, exhausted, wide);
         if (failed) {
             // its thresholds were counted by the generate kernel; the replay counts them again
             atomicAdd(&P.counters[kCntThresholds], 0ull - (unsigned long long)count);
             if (exhausted) atomicAdd(&P.counters[kCntExhausted], 1ull);
             registerSpill(P, tileIndex, column);
         }
+        // a unit with a thread for the wide pass is listed once (the flags are in the thread records)
+        const unsigned wideLanes = __ballot_sync(0xffffffffu, wide);
+        if (wideLanes && lane == __ffs((int)wideLanes) - 1) {
+            const unsigned int unitInTile = (unsigned int)column >> (5 - P.laneShift);
+            P.wideList[atomicAdd(P.work + kWorkWideCount, 1u)] = ((unsigned int)tileIndex << 8) | unitInTile;
+        }
     });
+}
+
+// The threads the slice kernel flagged kRecWide, sliced again with room for a run of kActiveCapWide thresholds per lane.
+// One warp per CTA (the scratch is most of the 48 KB of static shared memory); launched after every slice pass, it finds
+// its list empty on all but pathological frames.
+__global__ void __launch_bounds__(32) raster_slice_wide_kernel(const FrameParams P) {
+    __shared__ SliceScratchT<kActiveCapWide> W;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned int listed = P.work[kWorkWideCount];
+    if (listed == 0u) return;
+    if (lane == 0) { W.slabNext = 0u; W.slabEnd = 0u; }
+    __syncwarp();
+    ActiveRun q;
+    q.thr = W.aThr + lane;
+    q.hdr = W.aHdr + lane;
+    const int lanesPerUnit = 32 >> P.laneShift;
+    for (;;) {
+        unsigned int i = 0;
+        if (lane == 0) i = atomicAdd(P.work + kWorkWideCursor, 1u);
+        i = __shfl_sync(full, i, 0);
+        if (i >= listed) break;
+        const unsigned int entry = P.wideList[i];
+        const int tileIndex = (int)(entry >> 8);
+        const gudni_tile tile = P.tiles[tileIndex];
+        const int column = (int)((entry & 0xFFu) * (unsigned)lanesPerUnit) + min(lane, lanesPerUnit - 1);
+        ThreadRec* rec = lane < lanesPerUnit ? P.threadRecs + (((size_t)tileIndex << P.computeDepth) + (size_t)column) : nullptr;
+        if (rec && !(rec->pad1 & kRecWide)) rec = nullptr;   // the unit's other threads are done
+        if (rec) rec->pad1 &= ~kRecWide;
+        const unsigned int count = rec ? rec->count : 0u;
+        bool exhausted = false, wide = false;
+        const int failed = sliceWarp<kActiveCapWide>(P, W, q, tile, rec, column, exhausted, wide);
+        if (failed) {
+            atomicAdd(&P.counters[kCntThresholds], 0ull - (unsigned long long)count);
+            if (exhausted) atomicAdd(&P.counters[kCntExhausted], 1ull);
+            registerSpill(P, tileIndex, column);
+        }
+        __syncwarp();
+    }
 }
 
 #ifndef GUDNI_RESOLVE_WARPS
@@ -490,6 +535,7 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
         }
         P.refSlabBase = (unsigned int)b * regionSlabs;
         P.refCapSlabs = regionSlabs;
+        P.wideList = ctx->wideList.as<unsigned int>() + (size_t)b * ((size_t)(nTiles + batches - 1) / batches) * (size_t)(ctx->spec.threads_per_tile / 8);
         // units narrower than a warp when whole-warp units would not go round (see forEachUnit)
         long long units = (long long)tilesHere * (ctx->spec.threads_per_tile / 32);
         P.laneShift = 0;
@@ -500,11 +546,12 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
         raster_generate_kernel<<<std::min(ctx->genCtasPerSm * numSms, tilesHere), ctx->spec.threads_per_tile, genSmem, st>>>(P, firstTile, tilesHere);
         raster_sort_kernel<<<grid(ctx->sortCtasPerSm, kSortWarpsPerCta), kSortWarpsPerCta * 32, 0, st>>>(P, firstTile, tilesHere);
         raster_slice_kernel<<<grid(ctx->sliceCtasPerSm, kSliceWarpsPerCta), kSliceWarpsPerCta * 32, 0, st>>>(P, firstTile, tilesHere);
+        raster_slice_wide_kernel<<<numSms, 32, 0, st>>>(P);
         raster_resolve_kernel<<<grid(ctx->resolveCtasPerSm, kResolveWarpsPerCta), kResolveWarpsPerCta * 32, 0, st>>>(P, firstTile, tilesHere);
         raster_composite_kernel<<<ctx->compositeCtasPerSm * numSms, kCompositeWarpsPerCta * 32, 0, st>>>(P);
         raster_accumulate_kernel<<<grid(ctx->accumulateCtasPerSm, kAccumulateWarpsPerCta), kAccumulateWarpsPerCta * 32, 0, st>>>(P, firstTile, tilesHere);
         raster_picture_kernel<<<grid(ctx->colorCtasPerSm, kColorWarpsPerCta), kColorWarpsPerCta * 32, 0, st>>>(P, firstTile, tilesHere);
-        ctx->launches += 7;
+        ctx->launches += 8;
         GUDNI_CUDA_TRY(ctx, cudaGetLastError());
         if (b > 0) {
             GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evJoin[b - 1], st));

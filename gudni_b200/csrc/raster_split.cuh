@@ -68,12 +68,22 @@ constexpr unsigned int kSlabLow = 40;                      // refill when fewer 
 #endif
 constexpr int kActiveCap = GUDNI_ACTIVE_CAP;
 
-struct SliceScratch {
-    float4 aThr[kActiveCap * 32];    // (bottom, left, right, x of the cut)
-    uint32_t aHdr[kActiveCap * 32];
+template <int CAP>
+struct SliceScratchT {
+    float4 aThr[CAP * 32];           // (bottom, left, right, x of the cut)
+    uint32_t aHdr[CAP * 32];
     unsigned int slabNext, slabEnd;  // the warp's private range of pool chunks
     unsigned int pad[2];
 };
+using SliceScratch = SliceScratchT<kActiveCap>;
+// A run that outgrows kActiveCap is not lost to the lane-private replay at once: the slice kernel flags the thread and
+// lists its unit, and raster_slice_wide_kernel — one warp per CTA, a run of up to kActiveCapWide entries per lane —
+// slices the flagged threads of the listed units again before the colour passes start.  Only a run beyond that (or a
+// NaN) is replayed.
+#ifndef GUDNI_ACTIVE_CAP_WIDE
+#define GUDNI_ACTIVE_CAP_WIDE 72
+#endif
+constexpr int kActiveCapWide = GUDNI_ACTIVE_CAP_WIDE;   // 72 x 32 x 20 B = 46 KB of static shared memory
 
 struct ActiveRun {
     float4* thr;            // this lane's column of SliceScratch::aThr: entry e at thr[e * 32]
@@ -88,9 +98,10 @@ struct ActiveRun {
     int rem;                // remainders waiting in thr[0 .. rem), all starting at remTop
     float remTop;
     bool bad;               // NaN or capacity: replay the thread
+    bool wide;              // ... capacity: a run longer than the scratch holds
     __device__ __forceinline__ void attach(const float4* t, const uint32_t* h, unsigned int offset, int count) {
         sThr = t + offset; sHdr = h + offset; sNext = 0; sCount = count;
-        front = 0; rem = 0; remTop = FLT_MAX; runTop = 0.0f; cutY = 0.0f; bad = false;
+        front = 0; rem = 0; remTop = FLT_MAX; runTop = 0.0f; cutY = 0.0f; bad = false; wide = false;
         head = make_float4(FLT_MAX, FLT_MAX, 0.f, 0.f); headH = 0u;
         if (count > 0) { head = sThr[0]; headH = sHdr[0]; }
     }
@@ -126,7 +137,8 @@ struct ActiveRun {
 
 // Warp-converged: make sure the warp's slab holds at least `want` chunks (a lane that still runs dry inside a
 // round falls back to the global cursor).  What is left of the old slab is abandoned: address space, not traffic.
-__device__ __forceinline__ void ensureSlab(const FrameParams& P, SliceScratch& W, unsigned int want) {
+template <class WS>
+__device__ __forceinline__ void ensureSlab(const FrameParams& P, WS& W, unsigned int want) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
     if (lane == 0) {
@@ -145,19 +157,22 @@ struct StreamWriter {
     int pos;
     bool failed;           // the pool ran out
     unsigned int first;    // first chunk of the stream
-    __device__ __forceinline__ unsigned int alloc(const FrameParams& P, SliceScratch& W) {
+    template <class WS>
+    __device__ __forceinline__ unsigned int alloc(const FrameParams& P, WS& W) {
         unsigned int c = atomicAdd(&W.slabNext, 1u);
         if (c >= W.slabEnd) c = (unsigned int)atomicAdd(&P.counters[kCntStreamCursor], 1ull);
         return c;
     }
-    __device__ __forceinline__ void open(const FrameParams& P, SliceScratch& W) {
+    template <class WS>
+    __device__ __forceinline__ void open(const FrameParams& P, WS& W) {
         failed = false;
         pos = 0;
         first = alloc(P, W);
         if (first >= P.streamCapChunks) { failed = true; first = 0u; }
         chunk = P.streamPool + (size_t)first * kChunkRecs;
     }
-    __device__ __forceinline__ void put(const FrameParams& P, SliceScratch& W, uint32_t tag, uint32_t payload) {
+    template <class WS>
+    __device__ __forceinline__ void put(const FrameParams& P, WS& W, uint32_t tag, uint32_t payload) {
         if (failed) return;
         if (pos == kChunkRecs - 1) {   // the last slot of a chunk links to the next one
             const unsigned int c = alloc(P, W);
@@ -209,6 +224,7 @@ __device__ __forceinline__ void runToRemainders(ActiveRun& q, int numActive) {
 // splitNext = countActive + nextSlicePoint + sliceActive (K.cl:1007-1077): the thresholds that start at the queue's
 // smallest top become the run and are cut at the next event.  Returns the slice point; numActive = 0 and q.bad set
 // if the run does not fit.
+template <int CAP>
 __device__ __forceinline__ float formRun(ActiveRun& q, int& numActive) {
     const float top = fminf(q.rem > 0 ? q.remTop : FLT_MAX, q.head.x);
     int n = q.rem;
@@ -217,7 +233,7 @@ __device__ __forceinline__ float formRun(ActiveRun& q, int& numActive) {
     q.front = 0;
     // stored thresholds with the same top join the remainders, each behind every entry that is not strictly below it
     while (q.haveHead() && !(q.head.x > top)) {
-        if (n == kActiveCap) { q.bad = true; numActive = 0; return top; }
+        if (n == CAP) { q.bad = true; q.wide = true; numActive = 0; return top; }
         const Thr t{q.head.x, q.head.y, q.head.z, q.head.w};
         const uint32_t h = q.headH;
         int j = n;
@@ -259,7 +275,8 @@ __device__ __forceinline__ float formRun(ActiveRun& q, int& numActive) {
 // verticalAdvance, K.cl:1744-1824, without the shape stack: what it does to the stack (toggling the persistent
 // thresholds that cross the band border) goes into the stream as FLIP records; the un-toggling of the band that
 // ended (K.cl:1756-1759) is the resolve kernel resetting `cur` at the next first-of-band section.
-__device__ __forceinline__ void sliceVertical(const FrameParams& P, SliceScratch& W, StreamWriter& out, ActiveRun& q, SweepState& st,
+template <int CAP, class WS>
+__device__ __forceinline__ void sliceVertical(const FrameParams& P, WS& W, StreamWriter& out, ActiveRun& q, SweepState& st,
                                               float floatHeight) {
     st.gapTop = 0.0f;
     const float nextBreak = fminf(floatHeight, st.pixelY);
@@ -281,7 +298,7 @@ __device__ __forceinline__ void sliceVertical(const FrameParams& P, SliceScratch
             nextBottom = fminf(nextBreak, nextTop);
             st.gapTop = nextTop;   // nothing crosses the column above this y
         } else {
-            nextBottom = fminf(nextBreak, formRun(q, st.numActive));
+            nextBottom = fminf(nextBreak, formRun<CAP>(q, st.numActive));
             while (st.numActive > 0) {   // zero-height thresholds in front of the run: K.cl:1794-1799
                 if (q.runTop != q.upperBottom(q.front)) break;
                 const uint32_t h = q.upperHeader(q.front);
@@ -316,8 +333,10 @@ __device__ __forceinline__ void registerSpill(const FrameParams& P, int tileInde
 // One warp, one (tile, 32-column group) of a dense tile.  Returns per lane 1 if the thread has to be replayed
 // (a run outgrew the on-chip capacity, a NaN turned up, or the stream pool ran out: `exhausted`).
 // `rec`: the lane's thread record, null for a lane that has no column-thread in this unit (units narrower than a warp)
-__device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, ActiveRun& q, const gudni_tile& tile,
-                                         ThreadRec* recp, int column, bool& exhausted) {
+// `wide` (per lane): the thread only ran out of run capacity — raster_slice_wide_kernel takes it (see kActiveCapWide).
+template <int CAP, class WS>
+__device__ __forceinline__ int sliceWarp(const FrameParams& P, WS& W, ActiveRun& q, const gudni_tile& tile,
+                                         ThreadRec* recp, int column, bool& exhausted, bool& wide) {
     const unsigned full = 0xffffffffu;
     const ThreadGeom g = threadGeom(P, tile, column);
     const unsigned int recOffset = recp ? recp->offset : 0u, recCount = recp ? recp->count : kRecInactive;
@@ -358,7 +377,7 @@ __device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, 
                 }
             }
             if (st.alive) {
-                sliceVertical(P, W, out, q, st, floatHeight);
+                sliceVertical<CAP>(P, W, out, q, st, floatHeight);
                 if (q.bad) { spilled = true; st.alive = false; }
                 first = true;
                 blankRun = 1;
@@ -395,10 +414,13 @@ __device__ __forceinline__ int sliceWarp(const FrameParams& P, SliceScratch& W, 
         if (out.failed) st.alive = false;
     }
     exhausted = false;
+    wide = false;
     if (mine) {
         out.close();
         if (out.failed) { spilled = true; exhausted = true; }
         recp->chunk = out.first;
+        wide = spilled && q.wide && !out.failed && CAP < kActiveCapWide;
+        if (wide) { recp->pad1 |= kRecWide; return 0; }   // its thresholds stay where they are: sliced again with a longer run
         if (spilled) recp->count = kRecInactive;   // the later passes skip it; the replay renders the whole thread
     }
     return spilled ? 1 : 0;

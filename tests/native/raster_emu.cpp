@@ -178,6 +178,7 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
         const int batches = std::max(1, std::min({g_batches, kMaxBatches, nTiles}));
         const unsigned int regionSlabs = (unsigned int)refSlabs / (unsigned int)batches;
         unsigned int* work = reinterpret_cast<unsigned int*>(counters.data() + 32);
+        std::vector<unsigned int> wideList((size_t)(nTiles + kMaxBatches) * (size_t)(in.spec->threads_per_tile / 8));
         for (int b = 0; b < batches; b++) {
             const int tilesHere = (nTiles - b + batches - 1) / batches;
             P.work = work + (size_t)b * kWorkWords;
@@ -186,9 +187,11 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
             P.batchIndex = b;
             P.refSlabBase = (unsigned int)b * regionSlabs;
             P.refCapSlabs = regionSlabs;
+            P.wideList = wideList.data() + (size_t)b * ((size_t)(nTiles + batches - 1) / batches) * (size_t)(in.spec->threads_per_tile / 8);
             cuemu::launch(raster_generate_kernel, dim3(2), dim3(in.spec->threads_per_tile), P, 0, tilesHere);
             cuemu::launch(raster_sort_kernel, dim3(2), dim3(kSortWarpsPerCta * 32), P, 0, tilesHere);
             cuemu::launch(raster_slice_kernel, dim3(2), dim3(kSliceWarpsPerCta * 32), P, 0, tilesHere);
+            cuemu::launch(raster_slice_wide_kernel, dim3(2), dim3(32), P);
             cuemu::launch(raster_resolve_kernel, dim3(2), dim3(kResolveWarpsPerCta * 32), P, 0, tilesHere);
             cuemu::launch(raster_composite_kernel, dim3(2), dim3(kCompositeWarpsPerCta * 32), P);
             cuemu::launch(raster_accumulate_kernel, dim3(2), dim3(kAccumulateWarpsPerCta * 32), P, 0, tilesHere);

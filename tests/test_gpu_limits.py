@@ -40,6 +40,20 @@ def test_equal_sort_keys_keep_build_order(rasterizer, n):
     level1_parity(rasterizer, identical_shapes(n))
 
 
+def test_runs_past_the_slice_scratch_take_the_wide_pass(rasterizer):
+    """Runs of 13 to 72 thresholds that start together: flagged by the slice kernel, sliced again by
+    raster_slice_wide_kernel, no thread handed to the lane-private replay; a run of 73 still is."""
+    from test_kernels_emulated import identical_shapes
+    for n in (13, 50, 72):
+        img, stats, ref = level1_parity(rasterizer, identical_shapes(n))
+        assert stats.n_spilled_threads == 0, n
+    img, stats, ref = level1_parity(rasterizer, identical_shapes(73))
+    assert stats.n_spilled_threads > 0
+    # many units at once, mixed with ordinary ones
+    img, stats, ref = level2_parity(rasterizer, identical_shapes(40, width=700, height=300))
+    assert stats.n_spilled_threads == 0
+
+
 def test_very_long_queues_take_the_replay_path(rasterizer):
     # one shape of 150 thin rectangles on a 256-wide tile: every column-thread is 256 rows tall and crosses
     # ~300 thresholds, over the 256-entry on-chip capacity, under MAXTHRESHOLDS

@@ -168,6 +168,22 @@ def test_equal_keys_keep_the_order_they_were_built_in(emu, n):
     run(emu, identical_shapes(n))
 
 
+def test_runs_past_the_slice_kernels_scratch_take_the_wide_pass(emu):
+    """A run of more than 12 thresholds that start together does not fit the slice kernel's shared-memory scratch: the
+    thread is flagged, raster_slice_wide_kernel slices it again with room for 72, and only a longer run still goes to
+    the lane-private replay."""
+    assert run(emu, identical_shapes(12))[1] == 0
+    assert run(emu, identical_shapes(13))[1] == 0
+    assert run(emu, identical_shapes(50))[1] == 0
+    assert run(emu, identical_shapes(72))[1] == 0
+    assert run(emu, identical_shapes(73))[1] > 0
+    emu.raster_emu_set_batches(3)
+    try:
+        assert run(emu, identical_shapes(40, width=300, height=40))[1] == 0
+    finally:
+        emu.raster_emu_set_batches(1)
+
+
 def test_long_queues_take_the_bitonic_network(emu):
     stats = run(emu, scenes.thin_rectangles(100, width=64, spacing=2.0, thickness=0.9))
     assert stats[1] == 0                      # 128 < thresholds per column <= 256, still on chip
