@@ -415,7 +415,7 @@ namespace gudni_bin {
 
 static int log2ceil(int x) { int d = 0; while ((1 << d) < x) d++; return d; }
 
-int binScene(gudni_ctx* ctx, const gudni_shape_entry* devEntries, int n) {
+int binScene(gudni_ctx* ctx, const gudni_shape_entry* devEntries, int n, int (*whileBinning)(gudni_ctx*)) {
     const int canvasDepth = log2ceil(std::max(ctx->width, ctx->height));   // adjustedLog, TileTree.hs:74-75
     const int tileDepth = log2ceil(ctx->spec.max_tile_size);
     BinParams P{};
@@ -468,6 +468,8 @@ int binScene(gudni_ctx* ctx, const gudni_shape_entry* devEntries, int n) {
         bin_subdivide<<<(unsigned)nRoots, 256, 0, ctx->stream>>>(P); ctx->launches++;
         bin_leaf_scan<<<1, 1024, 0, ctx->stream>>>(P); ctx->launches++;
         GUDNI_CUDA_TRY(ctx, cudaGetLastError());
+        // the kernels above are queued: host work that can go on beside them (the upload of the geometry heap, shim.cu)
+        if (whileBinning) GUDNI_TRY(whileBinning(ctx));
         GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, P.counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
         GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (!host[kOverflow]) break;

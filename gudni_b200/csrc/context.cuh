@@ -112,6 +112,7 @@ struct gudni_ctx {
     // timing
     cudaEvent_t evFrameBegin = nullptr, evUploadDone = nullptr, evBinDone = nullptr, evRasterDone = nullptr,
                 evDownloadDone = nullptr, evFirstKernel = nullptr, evStrandsDone = nullptr, evGeometryUp = nullptr;
+    const void* geometryDeferredSrc = nullptr;   // frame_begin's geometry heap, not copied yet (the entries go first)
     bool geometryPending = false;   // the geometry heap is still crossing PCIe on the copy stream (waitGeometry, shim.cu)
     bool geometryTimed = false;     // ... this frame uploaded it there
     bool firstKernelRecorded = false;

@@ -136,6 +136,8 @@ int beginFrameCommon(gudni_ctx* ctx, const float bg[4], int width, int height, i
     ctx->firstKernelRecorded = false;
     ctx->binUsed = false;
     ctx->strandsUsed = false;
+    ctx->geometryDeferredSrc = nullptr;
+    ctx->geometryPending = ctx->geometryTimed = false;
     ctx->inFrame = true;
     GUDNI_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, 256, ctx->stream));
     return GUDNI_OK;
@@ -160,11 +162,29 @@ int uploadTo(gudni_ctx* ctx, DevBuf& buf, const void* src, size_t bytes, uint64_
 // The geometry heap is by far the largest input and the binning does not read it: it crosses PCIe on the copy stream
 // while the entries are uploaded and binned on the main one, and the first kernel that walks strands waits for it here.
 int waitGeometry(gudni_ctx* ctx) {
+    if (ctx->geometryDeferredSrc) {      // frame_begin only noted it: the entries go first (one copy engine serves both)
+        GUDNI_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evFrameBegin, 0));   // (after whatever the caller's stream still held)
+        GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->geometry.ptr, ctx->geometryDeferredSrc, ctx->geometryBytes, cudaMemcpyHostToDevice,
+                                            ctx->copyStream));
+        GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evGeometryUp, ctx->copyStream));
+        ctx->geometryDeferredSrc = nullptr;
+        ctx->geometryPending = true;
+        ctx->geometryTimed = true;
+        return GUDNI_OK;                 // the copy is on its way; the next call makes the main stream wait for it
+    }
     if (ctx->geometryPending) {
         GUDNI_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evGeometryUp, 0));
         ctx->geometryPending = false;
     }
     return GUDNI_OK;
+}
+
+// queue the deferred copy of the geometry heap, if any, without making the main stream wait for it yet
+int startGeometry(gudni_ctx* ctx) { return ctx->geometryDeferredSrc ? waitGeometry(ctx) : GUDNI_OK; }
+// ... and make the main stream wait for it
+int needGeometry(gudni_ctx* ctx) {
+    GUDNI_TRY(startGeometry(ctx));
+    return waitGeometry(ctx);
 }
 
 }  // namespace
@@ -265,13 +285,17 @@ int gudni_b200_frame_begin_cached(gudni_ctx* ctx, const void* geometry, size_t g
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evFrameBegin, ctx->stream));
     GUDNI_TRY(beginFrameCommon(ctx, background_rgba, width, height, frame_number));
-    bool copied = false;
-    GUDNI_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evFrameBegin, 0));   // (after whatever the caller's stream still holds)
-    GUDNI_TRY(uploadTo(ctx, ctx->geometry, geometry, geometry_bytes, gen->geometry, ctx->copyStream, &copied));
-    ctx->geometryTimed = copied;
-    if (copied) {
-        GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evGeometryUp, ctx->copyStream));
-        ctx->geometryPending = true;
+    // the geometry heap: sized (and looked up in the input cache) now, copied by startGeometry / waitGeometry
+    ctx->geometryTimed = false;
+    ctx->geometryPending = false;
+    ctx->geometryDeferredSrc = nullptr;
+    if (gen->geometry != 0 && ctx->geometry.ptr && ctx->geometry.generation == gen->geometry && ctx->geometry.bytesHeld == geometry_bytes) {
+        ctx->uploadsSkipped++;
+    } else {
+        GUDNI_TRY(devEnsure(ctx, ctx->geometry, std::max<size_t>(geometry_bytes, 16)));
+        if (geometry_bytes) ctx->geometryDeferredSrc = geometry;
+        ctx->geometry.generation = gen->geometry;
+        ctx->geometry.bytesHeld = geometry_bytes;
     }
     GUDNI_TRY(uploadTo(ctx, ctx->substances, substances, (size_t)n_substances * 16, gen->substances));
     GUDNI_TRY(uploadTo(ctx, ctx->pictures, picture_bytes, n_picture_bytes, gen->pictures));
@@ -338,7 +362,7 @@ static int launchPendingJobs(gudni_ctx* ctx) {
     GUDNI_TRY(ensureHandover(ctx, ctx->nTiles));
     markFirstKernel(ctx);
     GUDNI_TRY(devEnsure(ctx, ctx->strandBounds, ctx->geometryBytes / 2 + 16));
-    GUDNI_TRY(waitGeometry(ctx));
+    GUDNI_TRY(needGeometry(ctx));
     GUDNI_TRY(gudni_launch::strandBounds(ctx, ctx->geometryPtr, ctx->shapes.as<gudni_shape>() + ctx->rasteredShapes,
                                          (int)sizeof(gudni_shape), (int)(ctx->nShapes - ctx->rasteredShapes),
                                          ctx->strandBounds.as<float2>()));
@@ -402,9 +426,10 @@ static int rasterSceneCommon(gudni_ctx* ctx, const void* devEntries, int n_entri
     markFirstKernel(ctx);
     GUDNI_TRY(devEnsure(ctx, ctx->strandBounds, ctx->geometryBytes / 2 + 16));
     // binning first: it reads the entries only, so it runs while the geometry heap is still on its way (waitGeometry)
-    GUDNI_TRY(gudni_bin::binScene(ctx, static_cast<const gudni_shape_entry*>(devEntries), n_entries));
+    // (the copy of the geometry heap is queued once the first binning kernels are: startGeometry)
+    GUDNI_TRY(gudni_bin::binScene(ctx, static_cast<const gudni_shape_entry*>(devEntries), n_entries, startGeometry));
     GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evBinDone, ctx->stream));
-    GUDNI_TRY(waitGeometry(ctx));
+    GUDNI_TRY(needGeometry(ctx));
     GUDNI_TRY(gudni_launch::strandBounds(ctx, ctx->geometryPtr, devEntries, (int)sizeof(gudni_shape_entry), n_entries,
                                          ctx->strandBounds.as<float2>()));
     GUDNI_TRY(ensureDebug(ctx, 0, ctx->nColumns));
@@ -443,6 +468,7 @@ static int rasterOutlinesCommon(gudni_ctx* ctx, const void* devShapes, int n_sha
                                 const void* devPairs, const void* devTransforms, int64_t inputBytes) {
     GUDNI_TRY(ensureFrameBuffer(ctx));
     markFirstKernel(ctx);
+    GUDNI_TRY(needGeometry(ctx));   // (a heap handed to frame_begin is copied before this one replaces it, as it always was)
     GUDNI_TRY(gudni_launch::buildStrands(ctx, devShapes, n_shapes, devOutlines, devPairs, devTransforms));
     GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evStrandsDone, ctx->stream));
     ctx->strandsUsed = true;
@@ -502,7 +528,7 @@ int gudni_b200_debug_strands(gudni_ctx* ctx, void* geometry, size_t geometry_cap
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (geometry_bytes) *geometry_bytes = ctx->geometryBytes;
     if (n_entries) *n_entries = ctx->nEntries;
-    GUDNI_TRY(waitGeometry(ctx));
+    GUDNI_TRY(needGeometry(ctx));
     GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (geometry) {
         if (geometry_capacity < ctx->geometryBytes) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "debug_strands: geometry buffer too small");
@@ -524,7 +550,7 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     if (!ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "frame_end outside a frame");
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     GUDNI_TRY(ensureFrameBuffer(ctx));
-    GUDNI_TRY(waitGeometry(ctx));   // (a frame without raster calls: the caller's buffer must not be in use when this returns)
+    GUDNI_TRY(needGeometry(ctx));   // (a frame without raster calls: the caller's buffer must not be in use when this returns)
     if (ctx->nTiles) {
         GUDNI_TRY(launchPendingJobs(ctx));
         GUDNI_TRY(gudni_launch::rasterSpill(ctx, makeParams(ctx)));
