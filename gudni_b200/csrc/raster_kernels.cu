@@ -117,38 +117,27 @@ __global__ void __launch_bounds__(kSortWarpsPerCta * 32) raster_sort_kernel(cons
 // kept as a build option; it measured slower, see GUDNI_MAX_LANE_SHIFT.
 // body(tileIndex, tile, rec, column) is called by the whole warp for every unit of a dense tile; rec is the
 // lane's thread record, or null for a lane beyond the unit's width.
-// `group` (a power of two): consecutive units of a tile handed to the same warp, one after the other.  The resolve
-// kernel takes the slabs of a tile in groups so that its per-warp stack cache serves all of them (the same stacks lie
-// above and below a slab border); everything else runs with group = 1.
-// `which`: kAllTiles, or only the tiles that are (kSlabbedTiles) / are not (kFlatTiles) cut into at least four slabs —
-// grouping the units of a tile that is one slab of 256 rows would only serialize them.
-enum { kAllTiles = 0, kSlabbedTiles = 1, kFlatTiles = 2 };
 template <class F>
-__device__ __forceinline__ void forEachUnit(const FrameParams& P, int tileBase, int nTiles, int counterSlot, F body, int group = 1,
-                                            int which = kAllTiles) {
+__device__ __forceinline__ void forEachUnit(const FrameParams& P, int tileBase, int nTiles, int counterSlot, F body) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int unitShift = P.computeDepth - 5 + P.laneShift;            // units per tile
     const int lanesPerUnit = 32 >> P.laneShift;
     const unsigned totalUnits = (unsigned)nTiles << unitShift;
-    group = min(group, 1 << unitShift);
     const uint32_t denseCap = (uint32_t)min(P.maxShape, kWarpTableCap);
     unsigned int* workCounter = P.work + counterSlot;
     for (;;) {
-        unsigned first = 0;
-        if (lane == 0) first = atomicAdd(workCounter, (unsigned)group);
-        first = __shfl_sync(full, first, 0);
-        if (first >= totalUnits) break;
-        const int tileIndex = (int)P.tileOrder[tileBase + (int)(first >> unitShift) * P.batchStride + P.batchIndex];
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd(workCounter, 1u);
+        unit = __shfl_sync(full, unit, 0);
+        if (unit >= totalUnits) break;
+        const int tileIndex = (int)P.tileOrder[tileBase + (int)(unit >> unitShift) * P.batchStride + P.batchIndex];
+        const unsigned unitInTile = unit & ((1u << unitShift) - 1u);
         const gudni_tile tile = P.tiles[tileIndex];
         if (tile.shape_count > denseCap) continue;   // replayed lane-privately
-        if (which != kAllTiles && ((P.computeDepth - tile.h_depth >= 2) != (which == kSlabbedTiles))) continue;
-        for (unsigned unit = first; unit < first + (unsigned)group; unit++) {
-            const unsigned unitInTile = unit & ((1u << unitShift) - 1u);
-            const int column = (int)(unitInTile * (unsigned)lanesPerUnit) + min(lane, lanesPerUnit - 1);
-            ThreadRec* rec = lane < lanesPerUnit ? P.threadRecs + (((size_t)tileIndex << P.computeDepth) + (size_t)column) : nullptr;
-            body(tileIndex, tile, rec, column);
-        }
+        const int column = (int)(unitInTile * (unsigned)lanesPerUnit) + min(lane, lanesPerUnit - 1);
+        ThreadRec* rec = lane < lanesPerUnit ? P.threadRecs + (((size_t)tileIndex << P.computeDepth) + (size_t)column) : nullptr;
+        body(tileIndex, tile, rec, column);
     }
 }
 
@@ -240,10 +229,6 @@ __global__ void __launch_bounds__(32) raster_slice_wide_kernel(const FrameParams
 #define GUDNI_ACCUMULATE_WARPS 4
 #endif
 constexpr int kResolveWarpsPerCta = GUDNI_RESOLVE_WARPS;
-#ifndef GUDNI_RESOLVE_GROUP
-#define GUDNI_RESOLVE_GROUP 1         // measured on S4: 1: 10.61 ms, 2: 10.69, 4: 11.03, 8: 11.37 (same box) — S4's outlines cross every pixel
-#endif                                // about twice, so a slab's stacks are its own and the cache gains nothing from its neighbours
-constexpr int kResolveGroup = GUDNI_RESOLVE_GROUP;   // slabs of a tile one warp resolves in a row (forEachUnit)
 constexpr int kCompositeWarpsPerCta = GUDNI_COMPOSITE_WARPS;
 constexpr int kAccumulateWarpsPerCta = GUDNI_ACCUMULATE_WARPS;
 
@@ -252,7 +237,10 @@ __global__ void __launch_bounds__(kResolveWarpsPerCta * 32) raster_resolve_kerne
     __shared__ ResolveScratch scratch[kResolveWarpsPerCta];
     ResolveScratch& W = scratch[threadIdx.x >> 5];
     RefSlab slab{kRefNone, 0u, -1};
-    auto body = [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
+    // (A warp taking the slabs of a tile in groups of 2 / 4 / 8, so that its stack cache serves what lies above and below a
+    // slab border, measured slower on S4: 10.69 / 11.03 / 11.37 against 10.61 ms — S4's outlines cross every pixel about
+    // twice, a slab's stacks are its own.)
+    forEachUnit(P, tileBase, nTiles, kWorkResolve, [&](int tileIndex, const gudni_tile& tile, ThreadRec* rec, int column) {
         if (unitHasPictures(rec)) return;   // raster_picture_kernel
         const unsigned int count = rec ? rec->count : 0u;
         if (resolveWarp(P, W, slab, tileIndex, rec)) {
@@ -260,13 +248,7 @@ __global__ void __launch_bounds__(kResolveWarpsPerCta * 32) raster_resolve_kerne
             atomicAdd(&P.counters[kCntExhausted], 1ull);
             registerSpill(P, tileIndex, column);
         }
-    };
-    if (kResolveGroup > 1) {
-        forEachUnit(P, tileBase, nTiles, kWorkResolve, body, kResolveGroup, kSlabbedTiles);
-        forEachUnit(P, tileBase, nTiles, kWorkResolveFlat, body, 1, kFlatTiles);
-    } else {
-        forEachUnit(P, tileBase, nTiles, kWorkResolve, body);
-    }
+    });
     closeSlab(P, slab);
 }
 

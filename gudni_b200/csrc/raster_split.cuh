@@ -85,6 +85,7 @@ using SliceScratch = SliceScratchT<kActiveCap>;
 #endif
 constexpr int kActiveCapWide = GUDNI_ACTIVE_CAP_WIDE;   // 72 x 32 x 20 B = 46 KB of static shared memory
 
+constexpr int kBadOrder = 1, kBadCapacity = 2;
 struct ActiveRun {
     float4* thr;            // this lane's column of SliceScratch::aThr: entry e at thr[e * 32]
     uint32_t* hdr;
@@ -97,11 +98,10 @@ struct ActiveRun {
     int front;              // first entry of the run still active (zero-height ones in front are dropped, K.cl:1794-1799)
     int rem;                // remainders waiting in thr[0 .. rem), all starting at remTop
     float remTop;
-    bool bad;               // NaN or capacity: replay the thread
-    bool wide;              // ... capacity: a run longer than the scratch holds
+    int bad;                // kBadOrder: a NaN, replay the thread; kBadCapacity: a run longer than the scratch holds
     __device__ __forceinline__ void attach(const float4* t, const uint32_t* h, unsigned int offset, int count) {
         sThr = t + offset; sHdr = h + offset; sNext = 0; sCount = count;
-        front = 0; rem = 0; remTop = FLT_MAX; runTop = 0.0f; cutY = 0.0f; bad = false; wide = false;
+        front = 0; rem = 0; remTop = FLT_MAX; runTop = 0.0f; cutY = 0.0f; bad = 0;
         head = make_float4(FLT_MAX, FLT_MAX, 0.f, 0.f); headH = 0u;
         if (count > 0) { head = sThr[0]; headH = sHdr[0]; }
     }
@@ -233,7 +233,7 @@ __device__ __forceinline__ float formRun(ActiveRun& q, int& numActive) {
     q.front = 0;
     // stored thresholds with the same top join the remainders, each behind every entry that is not strictly below it
     while (q.haveHead() && !(q.head.x > top)) {
-        if (n == CAP) { q.bad = true; q.wide = true; numActive = 0; return top; }
+        if (n == CAP) { q.bad = kBadCapacity; numActive = 0; return top; }
         const Thr t{q.head.x, q.head.y, q.head.z, q.head.w};
         const uint32_t h = q.headH;
         int j = n;
@@ -267,7 +267,7 @@ __device__ __forceinline__ float formRun(ActiveRun& q, int& numActive) {
             nan = nan || (splitX != splitX);
         }
     }
-    if (nan) { q.bad = true; numActive = 0; return top; }
+    if (nan) { q.bad = kBadOrder; numActive = 0; return top; }
     numActive = n;
     return slicePoint;
 }
@@ -419,7 +419,7 @@ __device__ __forceinline__ int sliceWarp(const FrameParams& P, WS& W, ActiveRun&
         out.close();
         if (out.failed) { spilled = true; exhausted = true; }
         recp->chunk = out.first;
-        wide = spilled && q.wide && !out.failed && CAP < kActiveCapWide;
+        wide = spilled && q.bad == kBadCapacity && !out.failed && CAP < kActiveCapWide;
         if (wide) { recp->pad1 |= kRecWide; return 0; }   // its thresholds stay where they are: sliced again with a longer run
         if (spilled) recp->count = kRecInactive;   // the later passes skip it; the replay renders the whole thread
     }
