@@ -87,6 +87,8 @@ void runBlock(void (*entry)(void*), void* args, dim3 grid, dim3 block, uint3 bid
 #include "../../gudni_b200/csrc/strands.cu"
 
 #include <cstring>
+#include <set>
+#include <tuple>
 
 using namespace gudni_dev;
 
@@ -200,6 +202,20 @@ void rasterStage(const FrameInputs& in, const gudni_shape* shapes, int64_t nShap
         cuemu::launch(raster_spill_kernel, dim3(1), dim3(spillSlots), P, spillThr.data(), spillHdr.data(), spillSlots);
     }
     (void)nShapes;
+    if (getenv("GUDNI_EMU_STACKS")) {   // how well the resolve kernel's per-warp cache deduplicates: numbered stacks vs distinct (tile, stack) pairs
+        std::set<std::tuple<unsigned, unsigned long long, unsigned long long>> distinct;
+        unsigned long long numbered = 0;
+        const unsigned int* work = reinterpret_cast<const unsigned int*>(counters.data() + 32);
+        for (unsigned s = 0; s < work[kWorkRefSlabs] && s < P.refCapSlabs; s++) {
+            const uint2 info = refSlabInfo[s];
+            numbered += info.y;
+            for (unsigned i = 0; i < info.y; i++) {
+                const ulonglong2 k = stackKeys[(size_t)s * kRefSlab + i];
+                distinct.insert(std::make_tuple(info.x, k.x, k.y));
+            }
+        }
+        fprintf(stderr, "[emu] stacks numbered %llu, distinct per tile %zu, tiles %d\n", numbered, distinct.size(), nTiles);
+    }
     if (stats) {
         stats[0] = (int64_t)counters[kCntThresholds];
         stats[1] = (int64_t)counters[kCntSpilled];

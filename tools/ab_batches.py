@@ -8,7 +8,7 @@ import numpy as np  # noqa: E402
 from gudni_b200 import scenes  # noqa: E402
 from gudni_b200.raster import setup_rasterizer, DeviceScene  # noqa: E402
 
-settings = sys.argv[1:] or ["1", "2", "2o", "3o", "4o"]      # "3o": three ordered batches (GUDNI_BATCH_ORDERED)
+settings = sys.argv[1:] or ["1", "2", "2o", "3o", "4o"]      # "3o": three ordered batches (GUDNI_BATCH_ORDERED); "NAME=VALUE[,NAME=VALUE]": any environment
 frames = 8
 cases = [("s4", scenes.s4(), None), ("s5", scenes.s5(), None), ("s5_strip", None, (4608, 6656))]
 out = {}
@@ -17,8 +17,14 @@ for name, scene, strip in cases:
         scene = cases[1][1]
     ref = None
     for b in settings:
-        os.environ["GUDNI_BATCHES"] = b.rstrip("o")
-        os.environ["GUDNI_BATCH_ORDERED"] = "1" if b.endswith("o") else "0"
+        if "=" in b:
+            for kv in b.split(","):
+                k, v = kv.split("=")
+                if v == "": os.environ.pop(k, None)
+                else: os.environ[k] = v
+        else:
+            os.environ["GUDNI_BATCHES"] = b.rstrip("o")
+            os.environ["GUDNI_BATCH_ORDERED"] = "1" if b.endswith("o") else "0"
         r = setup_rasterizer()
         ent = scene.subset_rows(*strip) if strip else None
         d = DeviceScene(r, scene, entries=ent) if strip else DeviceScene(r, scene)
