@@ -185,8 +185,9 @@ __device__ __forceinline__ int originYOf(const BinParams& P, uint32_t rty) { ret
 // hands every node its place in the next frontier and its children's list space; (B) warp per
 // node: each lane tests one shape of the node's list against the cut and the survivors of each
 // half are compacted with ballot + popc prefix sums into the children's lists.
-__global__ void __launch_bounds__(256) bin_subdivide(const BinParams P) {
-    __shared__ uint32_t wN[8], wS[8];
+constexpr int kSubdivideThreads = 1024;   // 32 warps: a level's nodes are partitioned a warp each, and what a warp does is wait for loads
+__global__ void __launch_bounds__(kSubdivideThreads) bin_subdivide(const BinParams P) {
+    __shared__ uint32_t wN[32], wS[32];
     __shared__ uint32_t sNodes, sBase, sAnySplit, sAbort;
     const uint32_t root = blockIdx.x;
     uint32_t rtx, rty;
@@ -370,8 +371,12 @@ __global__ void __launch_bounds__(1024) bin_leaf_scan(const BinParams P) {
 // One CTA per root tile, one warp per leaf: the TileInfo record (Raster/Types.hs:176-198) with the
 // column allocation addTileToRasterJob would have given it (Raster/Job.hs:132-178), and the leaf's
 // Shape records newest-first (descending scene index) by rank sort.
+// (kEmitParts CTAs share a root tile's leaves: a frame has about as many root tiles as the chip has SMs, and one CTA per SM
+// leaves the rank sort waiting on its own loads.)
+constexpr unsigned kEmitParts = 4;
 __global__ void __launch_bounds__(256) bin_emit(const BinParams P) {
-    const uint32_t root = blockIdx.x;
+    const uint32_t parts = gridDim.x / (uint32_t)(P.rootsPerSide * P.rootsPerSide);   // 1 or kEmitParts (binScene)
+    const uint32_t root = blockIdx.x / parts, part = blockIdx.x % parts;
     const uint32_t nLeaves = P.leafCount[root];
     if (nLeaves == 0) return;
     uint32_t rtx, rty;
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(256) bin_emit(const BinParams P) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
     const BinNode* fin = P.frontier + (size_t)root * 2 * P.maxNodes + (size_t)P.rootCursor[root] * P.maxNodes;
     const uint32_t tileBase = P.tileOffset[root], shapeBase = P.shapeOffset[root];
-    for (uint32_t i = warp; i < nLeaves; i += nWarps) {
+    for (uint32_t i = part * nWarps + warp; i < nLeaves; i += nWarps * parts) {
         const BinNode n = fin[i];
         const uint32_t tileIdx = tileBase + i;
         const uint32_t shapeStart = shapeBase + n.outStart;
@@ -439,6 +444,10 @@ int binScene(gudni_ctx* ctx, const gudni_shape_entry* devEntries, int n, int (*w
     P.columnsPerTile = ctx->spec.max_tiles_per_call;
     if (P.rootsPerSide > 32768 / 1) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "canvas too large for the binning grid");
     const size_t nRoots = (size_t)P.rootsPerSide * P.rootsPerSide;
+    // A 4K frame is about as many root tiles as the chip has SMs, each with hundreds of shapes to split six levels deep: large
+    // CTAs (bin_subdivide) and several CTAs per root tile (bin_emit).  A 16K canvas is thousands of root tiles of a few dozen
+    // shapes that never split: small CTAs, one per root tile (S5: 0.09 ms against 0.21 the other way round).
+    const bool fewRoots = nRoots <= 512;
 
     GUDNI_TRY(devEnsure(ctx, ctx->binWork[0], nRoots * 8 * sizeof(uint32_t)));
     GUDNI_TRY(devEnsure(ctx, ctx->binWork[1], nRoots * 2 * (size_t)P.maxNodes * sizeof(BinNode)));
@@ -465,7 +474,7 @@ int binScene(gudni_ctx* ctx, const gudni_shape_entry* devEntries, int n, int (*w
         if (n) { bin_root_count<<<blocks, 256, 0, ctx->stream>>>(P); ctx->launches++; }
         bin_root_scan<<<1, 1024, 0, ctx->stream>>>(P); ctx->launches++;
         if (n) { bin_root_fill<<<blocks, 256, 0, ctx->stream>>>(P); ctx->launches++; }
-        bin_subdivide<<<(unsigned)nRoots, 256, 0, ctx->stream>>>(P); ctx->launches++;
+        bin_subdivide<<<(unsigned)nRoots, fewRoots ? kSubdivideThreads : 256, 0, ctx->stream>>>(P); ctx->launches++;
         bin_leaf_scan<<<1, 1024, 0, ctx->stream>>>(P); ctx->launches++;
         GUDNI_CUDA_TRY(ctx, cudaGetLastError());
         // the kernels above are queued: host work that can go on beside them (the upload of the geometry heap, shim.cu)
@@ -483,7 +492,7 @@ int binScene(gudni_ctx* ctx, const gudni_shape_entry* devEntries, int n, int (*w
     P.tiles = ctx->tiles.as<gudni_tile>();
     P.shapes = ctx->shapes.as<gudni_shape>();
     P.tileThreadBase = ctx->tileThreadBase.as<int32_t>();
-    bin_emit<<<(unsigned)nRoots, 256, 0, ctx->stream>>>(P); ctx->launches++;
+    bin_emit<<<(unsigned)nRoots * (fewRoots ? kEmitParts : 1u), 256, 0, ctx->stream>>>(P); ctx->launches++;
     GUDNI_CUDA_TRY(ctx, cudaGetLastError());
     ctx->nTiles = nTiles;
     ctx->nShapes = nRefs;

@@ -287,7 +287,7 @@ void binStage(const FrameInputs& in, const gudni_shape_entry* entries, int n, Bi
     P.tiles = out.tiles.data();
     P.shapes = out.shapes.data();
     P.tileThreadBase = out.threadBase.data();
-    cuemu::launch(bin_emit, dim3((unsigned)nRoots), dim3(256), P);
+    cuemu::launch(bin_emit, dim3((unsigned)nRoots * kEmitParts), dim3(256), P);
     out.tiles.resize(nTiles);
     out.shapes.resize(nRefs);
     out.threadBase.resize(nTiles);
