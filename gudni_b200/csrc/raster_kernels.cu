@@ -266,13 +266,13 @@ __global__ void __launch_bounds__(kCompositeWarpsPerCta * 32) raster_composite_k
         atomicMax(&P.counters[kCntRefSlabs], (unsigned long long)drawn * (unsigned long long)P.batchCount);
     unsigned int* workCounter = P.work + kWorkComposite;
     int tableTile = -1;
-    bool tame = false;
+    int mode = 0;
     for (;;) {
         unsigned int s = 0;
         if (lane == 0) s = atomicAdd(workCounter, 1u);
         s = __shfl_sync(full, s, 0);
         if (s >= nSlabs) break;
-        compositeSlab(P, T, tableTile, tame, P.refSlabBase + s);
+        compositeSlab(P, T, tableTile, mode, P.refSlabBase + s);
     }
 }
 

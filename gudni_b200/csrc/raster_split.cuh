@@ -607,12 +607,17 @@ struct TileTable {
     uint32_t meta[kWarpTableCap];        //   512 B
 };
 // fills the table (warp-cooperative); returns through the flags what kind of substances the tile lists
-__device__ __forceinline__ void buildTileTable(const FrameParams& P, TileTable& T, const gudni_tile& tile, bool& anyPicture, bool& anyWild) {
+// `plain` (may be null): every shape of the tile blends (add / continue tag) and their substance ids strictly rise or strictly
+// fall down the list — the usual case, a substance per shape handed out in scene order — so no two layers of a stack share a
+// substance and determineColor's "same substance as the layer above" test (K.cl:1476-1490) can never fire.
+__device__ __forceinline__ void buildTileTable(const FrameParams& P, TileTable& T, const gudni_tile& tile, bool& anyPicture, bool& anyWild,
+                                               bool* plain = nullptr) {
     const int lane = threadIdx.x & 31;
-    bool pic = false, wild = false;
+    bool pic = false, wild = false, allSet = true;
     for (uint32_t i = lane; i < tile.shape_count; i += 32) {
         const uint32_t meta = tagMeta(__ldg(&P.shapes[tile.shape_start + i].tag));
         T.meta[i] = meta;
+        allSet = allSet && (meta & kMetaSet) != 0u;
         pic = pic || (meta & kMetaPicture);
         float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!(meta & kMetaPicture)) {
@@ -624,6 +629,16 @@ __device__ __forceinline__ void buildTileTable(const FrameParams& P, TileTable& 
     }
     anyPicture = __any_sync(0xffffffffu, pic);
     anyWild = __any_sync(0xffffffffu, wild);
+    if (plain) {
+        __syncwarp();
+        bool rising = true, falling = true;
+        for (uint32_t i = lane; i + 1 < tile.shape_count; i += 32) {
+            const uint32_t a = T.meta[i] & kMetaIdMask, b = T.meta[i + 1] & kMetaIdMask;
+            rising = rising && a < b;
+            falling = falling && a > b;
+        }
+        *plain = __all_sync(0xffffffffu, allSet) && (__all_sync(0xffffffffu, rising) || __all_sync(0xffffffffu, falling));
+    }
 }
 
 // The tame walk is the composite kernel's inner loop (15.7 M stacks of ~38 layers per S4 frame, 95 % issue-active), so it
@@ -719,6 +734,26 @@ __device__ __forceinline__ float4 stackColorTame(const TileTable& T, uint64_t hi
 }
 #endif
 #endif
+// ... and for a plain tile (buildTileTable): every layer blends, nothing to remember from the layer above
+__device__ __forceinline__ float4 stackColorPlain(const TileTable& T, uint64_t hi, uint64_t lo, float4 bgPremul) {
+    float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f;
+    uint32_t word = (uint32_t)(hi >> 32);
+    int wordBase = 96;
+    for (;;) {
+        while (word == 0u) {
+            if (wordBase == 0) {
+                tameLayer(bx, by, bz, bw, bgPremul, true);
+                return make_float4(bx, by, bz, bw);
+            }
+            wordBase -= 32;
+            word = (wordBase == 64) ? (uint32_t)hi : (wordBase == 32) ? (uint32_t)(lo >> 32) : (uint32_t)lo;
+        }
+        const int b = 31 - __clz((int)word);
+        word ^= (1u << b);
+        tameLayer(bx, by, bz, bw, T.premul[wordBase + b], true);
+        if (bw == 1.0f) return make_float4(bx, by, bz, bw);
+    }
+}
 __device__ __forceinline__ float4 stackColorAny(const FrameParams& P, const TileTable& T, uint64_t hi, uint64_t lo, float4 bgPremul,
                                                 int absX, int absY) {
     float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -747,14 +782,20 @@ __device__ __forceinline__ float4 stackColorAny(const FrameParams& P, const Tile
 }
 
 // One warp, one slab of the stack table.
-__device__ __forceinline__ void compositeSlab(const FrameParams& P, TileTable& T, int& tableTile, bool& tame, unsigned int s) {
+// `mode` (warp-uniform, kept with the table): kWalkAny, kWalkTame or kWalkPlain
+enum { kWalkAny = 0, kWalkTame = 1, kWalkPlain = 2 };
+__device__ __forceinline__ void compositeSlab(const FrameParams& P, TileTable& T, int& tableTile, int& mode, unsigned int s) {
     const int lane = threadIdx.x & 31;
     const uint2 info = P.refSlabs[s];
     if ((int)info.x != tableTile) {
         __syncwarp();
-        bool anyPicture, anyWild;
-        buildTileTable(P, T, P.tiles[info.x], anyPicture, anyWild);
-        tame = !anyWild && substanceIsTame(P.background);
+        bool anyPicture, anyWild, plain;
+        buildTileTable(P, T, P.tiles[info.x], anyPicture, anyWild, &plain);
+        const bool tame = !anyWild && substanceIsTame(P.background);
+        mode = tame ? (plain ? kWalkPlain : kWalkTame) : kWalkAny;
+#ifdef GUDNI_NO_PLAIN_WALK
+        if (mode == kWalkPlain) mode = kWalkTame;
+#endif
         tableTile = (int)info.x;
         __syncwarp();
     }
@@ -762,7 +803,10 @@ __device__ __forceinline__ void compositeSlab(const FrameParams& P, TileTable& T
     for (unsigned int i = lane; i < info.y; i += 32) {
         const unsigned int ref = s * kRefSlab + i;
         const ulonglong2 key = P.stackKeys[ref];
-        const float4 c = tame ? stackColorTame(T, key.y, key.x, bgPremul) : stackColorAny(P, T, key.y, key.x, bgPremul, 0, 0);
+        float4 c;
+        if (mode == kWalkPlain) c = stackColorPlain(T, key.y, key.x, bgPremul);
+        else if (mode == kWalkTame) c = stackColorTame(T, key.y, key.x, bgPremul);
+        else c = stackColorAny(P, T, key.y, key.x, bgPremul, 0, 0);
         P.stackColors[ref] = c;
     }
 }

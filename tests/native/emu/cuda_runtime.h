@@ -242,6 +242,7 @@ template <class T> inline T __shfl_down_sync(unsigned m, T v, int d) { return cu
 template <class T> inline T __shfl_xor_sync(unsigned m, T v, int d) { return cuemu::unpack<T>(cuemu::collective(cuemu::kOpShflXor, m, cuemu::pack(v), d)); }
 inline unsigned __ballot_sync(unsigned m, int pred) { return (unsigned)cuemu::collective(cuemu::kOpBallot, m, pred ? 1 : 0, 0); }
 inline int __any_sync(unsigned m, int pred) { return cuemu::collective(cuemu::kOpBallot, m, pred ? 1 : 0, 0) != 0; }
+inline int __all_sync(unsigned m, int pred) { return cuemu::collective(cuemu::kOpBallot, m, pred ? 0 : 1, 0) == 0; }
 inline void __syncwarp(unsigned m = 0xFFFFFFFFu) { cuemu::collective(cuemu::kOpSync, m, 0, 0); }
 inline void __syncthreads() { cuemu::syncthreads(); }
 
