@@ -580,12 +580,12 @@ def run_native(args, rank, world, local_rank):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "the frame's raster kernels, one launch each: raster_generate_kernel, raster_sort_kernel, "
                                    "raster_slice_kernel, raster_resolve_kernel, raster_composite_kernel, raster_accumulate_kernel "
-                                   "(+ raster_picture_kernel, raster_spill_kernel); the dominant one is raster_slice_kernel "
-                                   "(profiles/r2_launches_s4.csv)", "kernel_ms": k_ms,
+                                   "(+ raster_slice_wide_kernel, raster_picture_kernel, raster_spill_kernel); the dominant one is raster_slice_kernel "
+                                   "(profiles/r2_launches_final.csv)", "kernel_ms": k_ms,
                          "bin_ms": float(np.mean(bin_ms)) if bin_ms else None, "algorithmic_bytes": int(a_bytes),
                          "note": "the path is instruction-issue / latency bound, not bandwidth bound: per S4 frame 14.1 M "
                                  "thresholds of curve subdivision, 19 M active runs, 75 M sweep sections, 15.7 M stack composites of "
-                                 "~38 layers; ncu per kernel in profiles/r2_s4_*.txt"},
+                                 "~38 layers; ncu per kernel in profiles/r2_final_*.txt"},
             "frame": stats.as_dict() if stats is not None else None,
         }
         if per_rank is not None:

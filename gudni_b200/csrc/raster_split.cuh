@@ -641,6 +641,16 @@ __device__ __forceinline__ void buildTileTable(const FrameParams& P, TileTable& 
     }
 }
 
+// index of the highest set bit of a non-zero word (one instruction; 31 - __clz() is three)
+__device__ __forceinline__ int topBit(uint32_t word) {
+#ifdef GUDNI_HOST_EMULATION
+    return 31 - __clz((int)word);
+#else
+    int b;
+    asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(word));
+    return b;
+#endif
+}
 // The tame walk is the composite kernel's inner loop (15.7 M stacks of ~38 layers per S4 frame, 95 % issue-active), so it
 // is written without branches inside a layer: the four words of the stack are walked by four copies of one loop, a layer
 // that does not blend (same substance as the one above, or not an add / continue tag) computes and discards, and
@@ -721,7 +731,7 @@ __device__ __forceinline__ float4 stackColorTame(const TileTable& T, uint64_t hi
             wordBase -= 32;
             word = (wordBase == 64) ? (uint32_t)hi : (wordBase == 32) ? (uint32_t)(lo >> 32) : (uint32_t)lo;
         }
-        const int b = 31 - __clz((int)word);
+        const int b = topBit(word);
         word ^= (1u << b);
         const int bit = wordBase + b;
         const uint32_t m = T.meta[bit];
@@ -739,6 +749,7 @@ __device__ __forceinline__ float4 stackColorPlain(const TileTable& T, uint64_t h
     float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f;
     uint32_t word = (uint32_t)(hi >> 32);
     int wordBase = 96;
+    const float4* premul = T.premul + 96;   // the word's 32 entries
     for (;;) {
         while (word == 0u) {
             if (wordBase == 0) {
@@ -746,11 +757,12 @@ __device__ __forceinline__ float4 stackColorPlain(const TileTable& T, uint64_t h
                 return make_float4(bx, by, bz, bw);
             }
             wordBase -= 32;
+            premul -= 32;
             word = (wordBase == 64) ? (uint32_t)hi : (wordBase == 32) ? (uint32_t)(lo >> 32) : (uint32_t)lo;
         }
-        const int b = 31 - __clz((int)word);
+        const int b = topBit(word);
         word ^= (1u << b);
-        tameLayer(bx, by, bz, bw, T.premul[wordBase + b], true);
+        tameLayer(bx, by, bz, bw, premul[b], true);
         if (bw == 1.0f) return make_float4(bx, by, bz, bw);
     }
 }
