@@ -54,6 +54,7 @@ struct gudni_ctx {
     DevBuf frame;
     void* externalTarget = nullptr;   // gudni_b200_frame_target
     int externalRowOrigin = 0;
+    const uint32_t* hostTarget = nullptr;   // gudni_b200_frame_target_host: the target is this page-locked host bitmap
 
     // counters / spill
     DevBuf counters;        // 8 x u64
@@ -78,8 +79,8 @@ struct gudni_ctx {
     unsigned long long refDemand = 0;          // slabs of stack numbers drawn last frame
     int spillSlots = 0;
     // a launch's tiles go through the kernels in `batches` interleaved batches, each on its own stream (rasterTiles)
-    int batches = 1;
-    bool batchOrdered = false;   // batches are runs of the cost order (the first one the most expensive tiles) instead of interleaved
+    int batches = 0;         // 0: chosen per launch (rasterTiles)
+    int batchOrdered = -1;   // batches are runs of the cost order (the first one the most expensive tiles) instead of interleaved; -1: chosen with `batches`
     std::vector<cudaStream_t> batchStreams;   // batches beyond the first
     std::vector<cudaEvent_t> evJoin;
     cudaEvent_t evFork = nullptr;

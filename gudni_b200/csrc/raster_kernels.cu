@@ -488,7 +488,13 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     }
     const int numSms = ctx->numSms;
     // Batches (FrameParams::work).  One batch per ~kBatchTiles tiles, at most kMaxBatches, or what GUDNI_BATCHES says.
-    int batches = ctx->batches > 0 ? ctx->batches : 1;
+    // One batch, except when the frame is stored into a canvas that is not this context's own (gudni_b200_frame_target: the
+    // presenting GPU's, over NVLink).  Then all ranks' accumulate kernels would push their strips into that GPU's inbound links
+    // at the same moment, at the end of the frame; with the cheap half of the tiles a batch of its own, that half's pixels
+    // cross while the expensive half is still being sliced (S5 on 8 GPUs: 3.95 -> 3.63 ms per frame; 4 / 8 batches 3.78 / 3.75).
+    // On a single GPU batches measured neutral to slower (profiles/README.md).
+    int batches = ctx->batches > 0 ? ctx->batches : (ctx->externalTarget ? 2 : 1);
+    const bool ordered = ctx->batchOrdered >= 0 ? ctx->batchOrdered != 0 : true;
     batches = std::max(1, std::min({batches, gudni_dev::kMaxBatches, nTiles}));
     GUDNI_TRY(ensureBatchStreams(ctx, batches));
     // work cursors of the kernels (the threshold store and stream cursors run on across the launches of a frame)
@@ -508,7 +514,7 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
         P.batchCount = batches;
         P.batchStride = batches;
         P.batchIndex = b;
-        if (ctx->batchOrdered) {
+        if (ordered) {
             const int lo = (int)((long long)nTiles * b / batches), hi = (int)((long long)nTiles * (b + 1) / batches);
             firstTile = tileBase + lo;
             tilesHere = hi - lo;

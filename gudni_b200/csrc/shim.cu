@@ -77,7 +77,7 @@ int ensureFrameBuffer(gudni_ctx* ctx) {
 // that runs one of them dry hands the threads that found it empty to the replay kernel and frame_end then
 // rasterizes the frame again with the measured demand (see retryExhausted), so an undersized guess costs time on
 // the first frame, never pixels.  One 32-byte record per thread.
-constexpr int kDefaultBatches = 1;
+constexpr int kDefaultBatches = 0;
 constexpr size_t kFirstGuessBudget = (size_t)6 << 30;
 int ensureHandover(gudni_ctx* ctx, int64_t totalTiles) {
     const size_t threads = (size_t)totalTiles * (size_t)ctx->spec.threads_per_tile;
@@ -230,9 +230,9 @@ int gudni_b200_init(int device, const gudni_spec* want, gudni_spec* got, gudni_c
     if (gudni_launch::strandTableInit(ctx) != GUDNI_OK) return fail(GUDNI_ERR_CUDA);
     if (devEnsure(ctx, ctx->counters, gudni_dev::kCountersBytes) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
     // batches per raster launch (rasterTiles): GUDNI_BATCHES overrides the default
-    ctx->batches = kDefaultBatches;
+    ctx->batches = kDefaultBatches;       // 0: rasterTiles decides (one batch, or two when the frame is stored into a peer's canvas)
     if (const char* e = std::getenv("GUDNI_BATCHES")) ctx->batches = std::max(1, std::min(atoi(e), gudni_dev::kMaxBatches));
-    if (const char* e = std::getenv("GUDNI_BATCH_ORDERED")) ctx->batchOrdered = atoi(e) != 0;
+    if (const char* e = std::getenv("GUDNI_BATCH_ORDERED")) ctx->batchOrdered = atoi(e) != 0 ? 1 : 0;
     ctx->spillCapacity = kSpillListCapacity;
     if (devEnsure(ctx, ctx->spillList, (size_t)kSpillListCapacity * 8) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
     ctx->spillSlots = kSpillSlots;
@@ -562,7 +562,7 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
     unsigned long long binCounters[8] = {0};
     for (int attempt = 0;; attempt++) {
         GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evRasterDone, ctx->stream));
-        if (out_bgra) {
+        if (out_bgra && out_bgra != ctx->hostTarget) {   // (a host target already holds the pixels: frame_target_host)
             const uint32_t* src = ctx->externalTarget
                                       ? static_cast<const uint32_t*>(ctx->externalTarget) +
                                             (size_t)(ctx->rowBegin - ctx->externalRowOrigin) * ctx->width
@@ -659,6 +659,23 @@ int gudni_b200_frame_target(gudni_ctx* ctx, void* dev_bgra, int row_origin) {
     if (row_origin < 0) return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "frame_target: negative row origin");
     ctx->externalTarget = dev_bgra;
     ctx->externalRowOrigin = dev_bgra ? row_origin : 0;
+    ctx->hostTarget = nullptr;
+    return GUDNI_OK;
+}
+
+int gudni_b200_frame_target_host(gudni_ctx* ctx, uint32_t* host_bgra) {
+    if (!ctx) return GUDNI_ERR_ARGUMENT;
+    if (ctx->nTiles && ctx->inFrame) return ctxFail(ctx, GUDNI_ERR_STATE, "frame_target_host after raster calls");
+    ctx->hostTarget = nullptr;
+    if (!host_bgra) return gudni_b200_frame_target(ctx, nullptr, 0);
+    GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void* dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, host_bgra, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return ctxFail(ctx, GUDNI_ERR_ARGUMENT, "frame_target_host: the bitmap is not page-locked (gudni_b200_host_register)");
+    }
+    GUDNI_TRY(gudni_b200_frame_target(ctx, dev, 0));
+    ctx->hostTarget = host_bgra;
     return GUDNI_OK;
 }
 
@@ -726,7 +743,7 @@ int gudni_b200_download(gudni_ctx* ctx, void* host_dst, const void* dev_src, siz
 int gudni_b200_host_register(gudni_ctx* ctx, void* host_ptr, size_t bytes) {
     if (!ctx || !host_ptr || !bytes) return GUDNI_ERR_ARGUMENT;
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    GUDNI_CUDA_TRY(ctx, cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    GUDNI_CUDA_TRY(ctx, cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
     return GUDNI_OK;
 }
 int gudni_b200_host_unregister(gudni_ctx* ctx, void* host_ptr) {

@@ -25,7 +25,7 @@ STATUS = {0: "GUDNI_OK", -1: "GUDNI_ERR_ARGUMENT", -2: "GUDNI_ERR_NO_DEVICE", -3
 # every symbol include/gudni_b200.h declares; tests check the library exports all of them
 ABI_SYMBOLS = [
     "gudni_b200_init", "gudni_b200_frame_begin", "gudni_b200_frame_strip", "gudni_b200_raster_job",
-    "gudni_b200_raster_scene", "gudni_b200_frame_end", "gudni_b200_frame_device_ptr", "gudni_b200_frame_target",
+    "gudni_b200_raster_scene", "gudni_b200_frame_end", "gudni_b200_frame_device_ptr", "gudni_b200_frame_target", "gudni_b200_frame_target_host",
     "gudni_b200_ipc_export_frame", "gudni_b200_ipc_open", "gudni_b200_ipc_close", "gudni_b200_device_alloc",
     "gudni_b200_device_free", "gudni_b200_host_register", "gudni_b200_host_unregister", "gudni_b200_upload", "gudni_b200_download", "gudni_b200_frame_begin_device",
     "gudni_b200_raster_scene_device", "gudni_b200_raster_outlines", "gudni_b200_raster_outlines_device",
@@ -71,6 +71,7 @@ def load_library():
     L.gudni_b200_frame_end.argtypes = [vp, vp, c.POINTER(CStats)]
     L.gudni_b200_frame_device_ptr.argtypes = [vp, c.POINTER(vp), c.POINTER(sz)]
     L.gudni_b200_frame_target.argtypes = [vp, vp, i32]
+    L.gudni_b200_frame_target_host.argtypes = [vp, vp]
     L.gudni_b200_set_stream.argtypes = [vp, vp]
     L.gudni_b200_ipc_export_frame.argtypes = [vp, vp]
     L.gudni_b200_ipc_open.argtypes = [vp, vp, c.POINTER(vp)]
@@ -307,6 +308,11 @@ class Rasterizer:
     def frame_target(self, dev_ptr, row_origin=0):
         self._check(self._L.gudni_b200_frame_target(self._ctx, ctypes.c_void_p(dev_ptr) if dev_ptr else None,
                                                     row_origin))
+
+    def frame_target_host(self, array):
+        """The kernels store the frame straight into `array` (uint32, height x width, page-locked with host_register);
+        frame_end(out=array) then copies nothing.  None restores the context's own frame buffer."""
+        self._check(self._L.gudni_b200_frame_target_host(self._ctx, array.ctypes.data if array is not None else None))
 
     def set_stream(self, cuda_stream):
         """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream) or None."""

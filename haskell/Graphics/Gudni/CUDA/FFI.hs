@@ -70,6 +70,12 @@ foreign import ccall safe "gudni_b200_host_register"
 foreign import ccall safe "gudni_b200_host_unregister"
   c_hostUnregister :: Ptr GudniCtx -> Ptr () -> IO CInt
 
+-- | Optional: make a page-locked HostBitmapTarget the frame's target, so that the kernels store their rows into it
+-- across PCIe while the rest of the frame is rasterized and c_frameEnd (given the same pointer) copies nothing.
+-- nullPtr restores the library's own frame buffer.
+foreign import ccall safe "gudni_b200_frame_target_host"
+  c_frameTargetHost :: Ptr GudniCtx -> Ptr CUInt -> IO CInt
+
 -- | Optional (multi-GPU hosts, one process per device): restrict the frame to whole root-tile rows
 -- [rowBegin, rowEnd) of the canvas; call between frame_begin and the raster calls.
 foreign import ccall safe "gudni_b200_frame_strip"

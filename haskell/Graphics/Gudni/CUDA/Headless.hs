@@ -46,8 +46,10 @@ withHostBitmap rasterizer w h body =
     ctx     = rasterCtx rasterizer
     acquire = do p <- mallocBytes bytes
                  checkStatus ctx =<< c_hostRegister ctx (castPtr p) (fromIntegral bytes)
+                 checkStatus ctx =<< c_frameTargetHost ctx p      -- the kernels store into it; frame_end copies nothing
                  return p
-    release p = do _ <- c_hostUnregister ctx (castPtr p)
+    release p = do _ <- c_frameTargetHost ctx nullPtr
+                   _ <- c_hostUnregister ctx (castPtr p)
                    free p
 
 -- | Binary PPM (P6), top row first.

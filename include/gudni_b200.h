@@ -260,6 +260,13 @@ int gudni_b200_frame_device_ptr(gudni_ctx* ctx, void** dev_bgra, size_t* n_bytes
  * CUDA IPC (row_origin = 0), so strips land on the presenting GPU over NVLink without a separate
  * gather.  NULL restores the context's own frame buffer. */
 int gudni_b200_frame_target(gudni_ctx* ctx, void* dev_bgra, int row_origin);
+/* The same for a bitmap in HOST memory: `host_bgra` — width * height words, page-locked through
+ * gudni_b200_host_register — becomes the frame's target, and the kernels store their finished rows into it
+ * across PCIe while the rest of the frame is still being rasterized, the way strips cross NVLink into a
+ * presenting GPU's canvas.  gudni_b200_frame_end called with the same pointer then has nothing left to copy
+ * (replaces the read-back of the OutputPtr target, OpenCL/Instances.hs:60-75, CallKernels.hs:196-201).  Stays
+ * in force until called with NULL; whole frames only (no gudni_b200_frame_strip). */
+int gudni_b200_frame_target_host(gudni_ctx* ctx, uint32_t* host_bgra);
 /* Run this context's work on a caller-owned CUDA stream (a cudaStream_t passed as void*), e.g.
  * torch's current stream so the caller's events bracket the kernels.  NULL restores the context's
  * own stream. */

@@ -153,3 +153,39 @@ def test_input_cache_skips_unchanged_uploads(rasterizer):
     fresh, _ = rasterizer.raster_scene(3, scene, generations=gens)
     plain, _ = rasterizer.raster_scene(4, scene)
     assert np.array_equal(fresh, plain) and not np.array_equal(fresh, first)
+
+
+def test_frame_stored_straight_into_a_host_bitmap(rasterizer):
+    """gudni_b200_frame_target_host: the kernels' pixel stores go to a page-locked host bitmap; frame_end with the same
+    pointer copies nothing; the pixels equal those of a frame rendered in HBM.  An unregistered bitmap is refused."""
+    scene = scenes.fuzzy_circles(400, 700, 500, 5, 60, 0x405)
+    ref, _ = rasterizer.raster_scene(0, scene)
+    host = np.zeros((scene.height, scene.width), np.uint32)
+    with pytest.raises(GudniError):
+        rasterizer.frame_target_host(host)
+    rasterizer.host_register(host)
+    try:
+        rasterizer.frame_target_host(host)
+        for frame in range(2):
+            host[:] = 0
+            out, stats = rasterizer.raster_scene(frame, scene, out=host)
+            assert np.array_equal(host, ref)
+        # pictures and the lane-private replay store pixels too
+        for other in (scenes.picture_scene(320, 300, flowers_size=(350, 200)),
+                      scenes.thin_rectangles(150, width=256, height=256, spacing=1.5, thickness=0.7, one_shape=True)):
+            rasterizer.frame_target_host(None)
+            want, _ = rasterizer.raster_scene(0, other)
+            small = np.zeros((other.height, other.width), np.uint32)
+            rasterizer.host_register(small)
+            try:
+                rasterizer.frame_target_host(small)
+                rasterizer.raster_scene(1, other, out=small)
+                assert np.array_equal(small, want)
+            finally:
+                rasterizer.frame_target_host(None)
+                rasterizer.host_unregister(small)
+    finally:
+        rasterizer.frame_target_host(None)
+        rasterizer.host_unregister(host)
+    again, _ = rasterizer.raster_scene(2, scene)
+    assert np.array_equal(again, ref)
