@@ -80,6 +80,7 @@ struct gudni_ctx {
     int spillSlots = 0;
     // a launch's tiles go through the kernels in `batches` interleaved batches, each on its own stream (rasterTiles)
     int batches = 0;         // 0: chosen per launch (rasterTiles)
+    int batchSplitPercent = 0;   // two ordered batches: the expensive batch's share of the tiles (0: half; GUDNI_BATCH_SPLIT)
     int batchOrdered = -1;   // batches are runs of the cost order (the first one the most expensive tiles) instead of interleaved; -1: chosen with `batches`
     std::vector<cudaStream_t> batchStreams;   // batches beyond the first
     std::vector<cudaEvent_t> evJoin;

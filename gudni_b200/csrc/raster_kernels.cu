@@ -504,6 +504,7 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
     ctx->launches++;
     if (batches > 1) GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
     const unsigned int regionSlabs = P.refCapSlabs / (unsigned int)batches;
+    size_t tilesBefore = 0;   // (the batches' regions of the wide list lie end to end)
     for (int b = 0; b < batches; b++) {
         cudaStream_t st = b == 0 ? ctx->stream : ctx->batchStreams[b - 1];
         if (b > 0) GUDNI_CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->evFork, 0));
@@ -515,7 +516,12 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
         P.batchStride = batches;
         P.batchIndex = b;
         if (ordered) {
-            const int lo = (int)((long long)nTiles * b / batches), hi = (int)((long long)nTiles * (b + 1) / batches);
+            int lo = (int)((long long)nTiles * b / batches), hi = (int)((long long)nTiles * (b + 1) / batches);
+            if (batches == 2 && ctx->batchSplitPercent > 0) {   // the expensive batch's share of the tiles
+                const int cut = std::max(1, std::min(nTiles - 1, (int)((long long)nTiles * ctx->batchSplitPercent / 100)));
+                lo = b == 0 ? 0 : cut;
+                hi = b == 0 ? cut : nTiles;
+            }
             firstTile = tileBase + lo;
             tilesHere = hi - lo;
             P.batchStride = 1;
@@ -523,7 +529,8 @@ int rasterTiles(gudni_ctx* ctx, const FrameParams& frame, int tileBase, int nTil
         }
         P.refSlabBase = (unsigned int)b * regionSlabs;
         P.refCapSlabs = regionSlabs;
-        P.wideList = ctx->wideList.as<unsigned int>() + (size_t)b * ((size_t)(nTiles + batches - 1) / batches) * (size_t)(ctx->spec.threads_per_tile / 8);
+        P.wideList = ctx->wideList.as<unsigned int>() + tilesBefore * (size_t)(ctx->spec.threads_per_tile / 8);
+        tilesBefore += (size_t)tilesHere;
         // units narrower than a warp when whole-warp units would not go round (see forEachUnit)
         long long units = (long long)tilesHere * (ctx->spec.threads_per_tile / 32);
         P.laneShift = 0;

@@ -233,6 +233,7 @@ int gudni_b200_init(int device, const gudni_spec* want, gudni_spec* got, gudni_c
     ctx->batches = kDefaultBatches;       // 0: rasterTiles decides (one batch, or two when the frame is stored into a peer's canvas)
     if (const char* e = std::getenv("GUDNI_BATCHES")) ctx->batches = std::max(1, std::min(atoi(e), gudni_dev::kMaxBatches));
     if (const char* e = std::getenv("GUDNI_BATCH_ORDERED")) ctx->batchOrdered = atoi(e) != 0 ? 1 : 0;
+    if (const char* e = std::getenv("GUDNI_BATCH_SPLIT")) ctx->batchSplitPercent = std::max(0, std::min(atoi(e), 99));
     ctx->spillCapacity = kSpillListCapacity;
     if (devEnsure(ctx, ctx->spillList, (size_t)kSpillListCapacity * 8) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
     ctx->spillSlots = kSpillSlots;
