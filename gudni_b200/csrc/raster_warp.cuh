@@ -136,6 +136,8 @@ struct SearchSummaries {
     uint32_t* flags;   // kItem*
 };
 constexpr uint32_t kItemInRange = 1u, kItemPersistentAbove = 2u, kItemNoNaN = 4u;
+// where the two searches ended (Trav::idx), when both fit a byte: bits 8-15 and 16-23 (strandSearchFrom)
+constexpr uint32_t kItemEnds = 8u;
 __host__ __device__ constexpr size_t searchSummariesBytes() { return (size_t)kGenItems * 12; }
 
 // Whole CTA.  Afterwards q holds the thread's thresholds in push order (or t.failed is set).
@@ -272,6 +274,9 @@ __device__ __forceinline__ void generateTileThresholds(const FrameParams& P, Til
                     const float ymax = fmaxf(fmaxf(fmaxf(l.ly, l.cy), fmaxf(l.ry, r.ly)), fmaxf(r.cy, r.ry));
                     const bool noNaN = (l.ly == l.ly) && (l.cy == l.cy) && (l.ry == l.ry) && (r.ly == r.ly) && (r.cy == r.cy) && (r.ry == r.ry);
                     flags = kItemInRange | (strandPersistentAbove(l, r) ? kItemPersistentAbove : 0u) | (noNaN ? kItemNoNaN : 0u);
+#ifndef GUDNI_NO_SEARCH_ENDS
+                    if (l.idx < 256 && r.idx < 256) flags |= kItemEnds | ((uint32_t)l.idx << 8) | ((uint32_t)r.idx << 16);
+#endif
                     R.yRange[item] = make_float2(ymin, ymax);
                 }
             }
@@ -307,7 +312,12 @@ __device__ __forceinline__ void generateTileThresholds(const FrameParams& P, Til
                 const StrandEntry& en = S.entry[k];
                 const uint32_t n = en.shapeAndFlags & kEntryShapeMask;
                 Trav l, r;
-                strandSearch(P.geometry + 16ull * en.offset16, en.sizeWord, ox, en.right, en.lc, l, r);   // in range: see B
+                const uint32_t found = R.flags[(k << tile.h_depth) + column];
+                if (found & kItemEnds)
+                    strandSearchFrom(P.geometry + 16ull * en.offset16, ox, en.right, en.lc, (int)((found >> 8) & 0xFFu),
+                                     (int)((found >> 16) & 0xFFu), l, r);
+                else
+                    strandSearch(P.geometry + 16ull * en.offset16, en.sizeWord, ox, en.right, en.lc, l, r);   // in range: see B
                 l.ly -= oy; l.cy -= oy; l.ry -= oy;
                 r.ly -= oy; r.cy -= oy; r.ry -= oy;
                 GenFlags f{false, false};
