@@ -1,7 +1,7 @@
 """The kernels under sanitizers, CPU only: builds the host SIMT emulation of the CUDA kernels
 (tests/native/raster_emu.cpp) with -fsanitize=undefined or -fsanitize=address and runs the emulated-kernel
-scenarios of tests/test_kernels_emulated.py through it (catalogue, circles, pictures, both spill paths,
-levels 2 and 3, refused frames).  Global and shared memory are host heap / static arrays there, so an out-of-bounds access or a
+scenarios of tests/test_kernels_emulated.py through it (catalogue, circles, pictures, both spill paths, the wide
+slice pass, launches in batches, levels 2 and 3, refused frames).  Global and shared memory are host heap / static arrays there, so an out-of-bounds access or a
 misaligned vector load in a kernel is reported like any host bug.
 
     python tools/emu_sanitize.py ubsan|asan
@@ -35,6 +35,16 @@ def scenario(lib_path):
     T.run(L, scenes.picture_scene(320, 300, flowers_size=(350, 200)))
     T.run(L, scenes.thin_rectangles(150, width=256, height=256, spacing=1.5, thickness=0.7, one_shape=True))
     T.run(L, scenes.fuzzy_circles(1200, 96, 96, 5, 50, 77))
+    # runs past the slice kernel's scratch (raster_slice_wide_kernel: its list, its 72-entry scratch, the overflow beyond)
+    for n in (13, 50, 72, 73):
+        T.run(L, T.identical_shapes(n))
+    # a launch in batches: own work cursors, own regions of the stack table and of the wide list
+    for batches in (2, 3, 8):
+        L.raster_emu_set_batches(batches)
+        T.run(L, scenes.fuzzy_circles(150, 200, 150, 4, 40, 6))
+        T.run(L, T.identical_shapes(40, width=300, height=40))
+        T.run(L, scenes.picture_scene(320, 300, flowers_size=(350, 200)))
+    L.raster_emu_set_batches(1)
     for level in (2, 3):
         T.run_scene(L, scenes.mixed_bag(100, 300, 200, 7003), level)
         T.run_scene(L, scenes.fuzzy_circles(400, 150, 130, 5, 40, 0x1234), level, RasterSpec(64, 64, 64, 256, 254, 127))
