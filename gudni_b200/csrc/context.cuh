@@ -13,6 +13,9 @@
 #include <vector>
 
 #include "../../include/gudni_b200.h"
+#ifndef GUDNI_HOST_EMULATION   // (the emulated kernels need nothing of the host side)
+#include "hostcopy.cuh"
+#endif
 
 struct DevBuf {
     void* ptr = nullptr;
@@ -107,6 +110,11 @@ struct gudni_ctx {
     int64_t outlineInputBytes = 0;
     bool strandsUsed = false;
 
+    // pageable caller memory <-> device through page-locked staging and a few copy threads (hostcopy.cuh)
+#ifndef GUDNI_HOST_EMULATION
+    HostCopier copier;
+#endif
+    int copyThreads = 4;     // GUDNI_COPY_THREADS; 0: leave pageable memory to the driver
     // pinned staging for host transfers
     void* pinned = nullptr;
     size_t pinnedCap = 0;

@@ -143,6 +143,26 @@ int beginFrameCommon(gudni_ctx* ctx, const float bg[4], int width, int height, i
     return GUDNI_OK;
 }
 
+// host -> device on `stream`: pageable memory of some size through the context's staging ring and copy threads
+// (hostcopy.cuh), everything else as it is
+int copyIn(gudni_ctx* ctx, void* dev, const void* host, size_t bytes, cudaStream_t stream) {
+    if (bytes >= HostCopier::kWorthIt && ctx->copyThreads > 0 && HostCopier::pageable(host) && ctx->copier.start(ctx->copyThreads)) {
+        GUDNI_CUDA_TRY(ctx, ctx->copier.upload(dev, host, bytes, stream));
+        return GUDNI_OK;
+    }
+    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, stream));
+    return GUDNI_OK;
+}
+// device -> host on `stream` (queued; for pageable memory: done when this returns)
+int copyOut(gudni_ctx* ctx, void* host, const void* dev, size_t bytes, cudaStream_t stream) {
+    if (bytes >= HostCopier::kWorthIt && ctx->copyThreads > 0 && HostCopier::pageable(host) && ctx->copier.start(ctx->copyThreads)) {
+        GUDNI_CUDA_TRY(ctx, ctx->copier.download(host, dev, bytes, stream));
+        return GUDNI_OK;
+    }
+    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, stream));
+    return GUDNI_OK;
+}
+
 // `generation` != 0: skip the copy if the buffer already holds `bytes` bytes uploaded under that generation
 int uploadTo(gudni_ctx* ctx, DevBuf& buf, const void* src, size_t bytes, uint64_t generation = 0, cudaStream_t stream = nullptr,
              bool* copied = nullptr) {
@@ -152,7 +172,7 @@ int uploadTo(gudni_ctx* ctx, DevBuf& buf, const void* src, size_t bytes, uint64_
         return GUDNI_OK;
     }
     GUDNI_TRY(devEnsure(ctx, buf, std::max<size_t>(bytes, 16)));
-    if (bytes) GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(buf.ptr, src, bytes, cudaMemcpyHostToDevice, stream ? stream : ctx->stream));
+    if (bytes) GUDNI_TRY(copyIn(ctx, buf.ptr, src, bytes, stream ? stream : ctx->stream));
     if (copied) *copied = bytes != 0;
     buf.generation = generation;
     buf.bytesHeld = bytes;
@@ -164,8 +184,7 @@ int uploadTo(gudni_ctx* ctx, DevBuf& buf, const void* src, size_t bytes, uint64_
 int waitGeometry(gudni_ctx* ctx) {
     if (ctx->geometryDeferredSrc) {      // frame_begin only noted it: the entries go first (one copy engine serves both)
         GUDNI_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evFrameBegin, 0));   // (after whatever the caller's stream still held)
-        GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->geometry.ptr, ctx->geometryDeferredSrc, ctx->geometryBytes, cudaMemcpyHostToDevice,
-                                            ctx->copyStream));
+        GUDNI_TRY(copyIn(ctx, ctx->geometry.ptr, ctx->geometryDeferredSrc, ctx->geometryBytes, ctx->copyStream));
         GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evGeometryUp, ctx->copyStream));
         ctx->geometryDeferredSrc = nullptr;
         ctx->geometryPending = true;
@@ -233,6 +252,7 @@ int gudni_b200_init(int device, const gudni_spec* want, gudni_spec* got, gudni_c
     ctx->batches = kDefaultBatches;       // 0: rasterTiles decides (one batch, or two when the frame is stored into a peer's canvas)
     if (const char* e = std::getenv("GUDNI_BATCHES")) ctx->batches = std::max(1, std::min(atoi(e), gudni_dev::kMaxBatches));
     if (const char* e = std::getenv("GUDNI_BATCH_ORDERED")) ctx->batchOrdered = atoi(e) != 0 ? 1 : 0;
+    if (const char* e = std::getenv("GUDNI_COPY_THREADS")) ctx->copyThreads = std::max(0, std::min(atoi(e), 16));
     if (const char* e = std::getenv("GUDNI_BATCH_SPLIT")) ctx->batchSplitPercent = std::max(0, std::min(atoi(e), 99));
     ctx->spillCapacity = kSpillListCapacity;
     if (devEnsure(ctx, ctx->spillList, (size_t)kSpillListCapacity * 8) != GUDNI_OK) return fail(GUDNI_ERR_OOM);
@@ -568,7 +588,7 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
                                       ? static_cast<const uint32_t*>(ctx->externalTarget) +
                                             (size_t)(ctx->rowBegin - ctx->externalRowOrigin) * ctx->width
                                       : ctx->frame.as<uint32_t>();
-            GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(out_bgra, src, rows * ctx->width * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            GUDNI_TRY(copyOut(ctx, out_bgra, src, rows * ctx->width * 4, ctx->stream));
         }
         GUDNI_CUDA_TRY(ctx, cudaEventRecord(ctx->evDownloadDone, ctx->stream));
         GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(counters, ctx->counters.ptr, 256, cudaMemcpyDeviceToHost, ctx->stream));
