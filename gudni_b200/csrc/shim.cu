@@ -750,14 +750,14 @@ int gudni_b200_device_free(gudni_ctx* ctx, void* dev_ptr) {
 int gudni_b200_upload(gudni_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes) {
     if (!ctx || (bytes && (!dev_dst || !host_src))) return GUDNI_ERR_ARGUMENT;
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) GUDNI_TRY(copyIn(ctx, dev_dst, host_src, bytes, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return GUDNI_OK;
 }
 int gudni_b200_download(gudni_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
     if (!ctx || (bytes && (!host_dst || !dev_src))) return GUDNI_ERR_ARGUMENT;
     GUDNI_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bytes) GUDNI_TRY(copyOut(ctx, host_dst, dev_src, bytes, ctx->stream));
     GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return GUDNI_OK;
 }

@@ -189,3 +189,35 @@ def test_frame_stored_straight_into_a_host_bitmap(rasterizer):
         rasterizer.host_unregister(host)
     again, _ = rasterizer.raster_scene(2, scene)
     assert np.array_equal(again, ref)
+
+
+def test_pageable_transfers_through_the_staging_ring(rasterizer):
+    """Transfers of a megabyte and more between pageable memory and the device go through the context's own page-locked
+    ring, copied by several threads (hostcopy.cuh): sizes around the chunk and ring boundaries, uploads back to back
+    (a staging buffer is reused only when the DMA that read it is done), page-locked memory beside them."""
+    L, ctx = rasterizer._L, rasterizer._ctx
+    rng = np.random.default_rng(0xC0B1)
+    chunk = 4 << 20
+    sizes = [1 << 20, (1 << 20) + 1, chunk - 1, chunk, chunk + 4097, 4 * chunk, 4 * chunk + 3, 9 * chunk + 12345, 1000]
+    bufs = []
+    for n in sizes:
+        host = rng.integers(0, 256, n, dtype=np.uint8)
+        p = ctypes.c_void_p()
+        assert L.gudni_b200_device_alloc(ctx, n, ctypes.byref(p)) == 0
+        bufs.append((host, p))
+    for host, p in bufs:                  # all uploads first: the ring wraps around several times
+        assert L.gudni_b200_upload(ctx, p, host.ctypes.data, host.nbytes) == 0
+    for host, p in reversed(bufs):
+        back = np.zeros_like(host)
+        assert L.gudni_b200_download(ctx, back.ctypes.data, p, host.nbytes) == 0
+        assert np.array_equal(back, host), host.nbytes
+    host, p = bufs[-2]
+    pinned = np.zeros_like(host)
+    rasterizer.host_register(pinned)
+    try:
+        assert L.gudni_b200_download(ctx, pinned.ctypes.data, p, host.nbytes) == 0
+        assert np.array_equal(pinned, host)
+    finally:
+        rasterizer.host_unregister(pinned)
+    for host, p in bufs:
+        assert L.gudni_b200_device_free(ctx, p) == 0
