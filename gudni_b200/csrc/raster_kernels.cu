@@ -22,7 +22,8 @@ using namespace gudni_dev;
 constexpr int kSliceWarpsPerCta = GUDNI_SLICE_WARPS;
 constexpr int kColorWarpsPerCta = GUDNI_COLOR_WARPS;
 
-// A frame (or a launch of up to kLaunchTiles tiles of it) goes through seven kernels on one stream; every one sizes
+// A frame (or a launch of up to kLaunchTiles tiles of it) goes through these kernels on one stream (on two, as two batches
+// of tiles, when its pixels leave the GPU: rasterTiles); every one sizes
 // its grid to what the chip holds resident and pulls its work from a global counter, expensive tiles first:
 //   raster_generate_kernel    generateThresholds (K.cl:2030-2082), one CTA per tile: the column-threads' threshold
 //                             queues packed into HBM (20 B per threshold)
