@@ -15,7 +15,8 @@ using gudni_dev::FrameParams;
 namespace {
 
 constexpr int kSpillListCapacity = 1 << 22;   // column-threads that may leave the on-chip queue per frame
-constexpr int kSpillSlots = 148 * 128;        // HBM queue slots of the replay kernel (one CTA of 128 per SM)
+constexpr int kSpillSlots = 148 * 128;        // HBM queue slots of the replay kernel (one CTA of 128 per SM) to start with
+constexpr int kSpillSlotsMax = 148 * 128 * 8; // ... and at most (a frame that replays many threads: see frame_end)
 
 bool isPow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 int log2i(int x) { int d = 0; while ((1 << d) < x) d++; return d; }
@@ -595,6 +596,19 @@ int gudni_b200_frame_end(gudni_ctx* ctx, uint32_t* out_bgra, gudni_stats* stats)
         if (ctx->binUsed)
             GUDNI_CUDA_TRY(ctx, cudaMemcpyAsync(binCounters, ctx->binCounters.ptr, 64, cudaMemcpyDeviceToHost, ctx->stream));
         GUDNI_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        // A frame that sends many threads to the lane-private replay (tiles over MAXSHAPE at the 8-pixel floor, queues over the
+        // on-chip capacity) finds it four warps per SM wide: its HBM queues are per slot, and a context starts with few.  The
+        // next frame gets a slot for every such thread, up to eight CTAs per SM (20,000 circles on 512 x 512: 646 -> 328 ms at
+        // four CTAs per SM).
+        if (counters[gudni_dev::kCntSpilled] > (unsigned long long)ctx->spillSlots && ctx->spillSlots < kSpillSlotsMax) {
+            int slots = ctx->spillSlots;
+            while (slots < kSpillSlotsMax && (unsigned long long)slots < counters[gudni_dev::kCntSpilled]) slots *= 2;
+            if (devEnsure(ctx, ctx->spillThr, (size_t)slots * ctx->spec.max_thresholds * 16) == GUDNI_OK &&
+                devEnsure(ctx, ctx->spillHdr, (size_t)slots * ctx->spec.max_thresholds * 4) == GUDNI_OK)
+                ctx->spillSlots = slots;
+            else
+                ctx->err.clear();   // (no room: the replay stays as narrow as it was)
+        }
         ctx->storeDemand = counters[gudni_dev::kCntStoreCursor];
         ctx->streamDemand = counters[gudni_dev::kCntStreamCursor];
         ctx->refDemand = counters[gudni_dev::kCntRefSlabs];
