@@ -307,10 +307,14 @@ __global__ void __launch_bounds__(kColorWarpsPerCta * 32) raster_picture_kernel(
 // regardless of how many threads spilled.
 __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, float4* thr, uint32_t* hdr, int slots) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     unsigned long long n = P.counters[kCntSpilled];
     if (n > (unsigned long long)P.spillCapacity) n = (unsigned long long)P.spillCapacity;
-    for (unsigned long long i = slot; i < n; i += (unsigned long long)slots) {
-        const unsigned long long packed = P.spillList[i];
+    // (warp-uniform trip count: the lanes of a warp colour their sections together, rasterThread)
+    for (unsigned long long first = (unsigned long long)(slot - lane); first < n; first += (unsigned long long)slots) {
+        const unsigned long long i = first + (unsigned long long)lane;
+        const bool active = i < n;
+        const unsigned long long packed = active ? P.spillList[i] : 0ull;
         const int tileIndex = (int)(packed >> 32), column = (int)(packed & 0xFFFFFFFFull);
         const gudni_tile tile = P.tiles[tileIndex];
         const ThreadGeom g = threadGeom(P, tile, column);
@@ -321,9 +325,9 @@ __global__ void __launch_bounds__(128) raster_spill_kernel(const FrameParams P, 
         q.cap = P.maxThresholds;
         // the first kernel does not count the thresholds of a thread it hands over
         int generated;
-        bool ok = rasterThread(P, g, q, P.tileThreadBase[tileIndex] + column, generated);
-        if (generated > 0) atomicAdd(&P.counters[kCntThresholds], (unsigned long long)generated);
-        if (!ok) atomicAdd(&P.counters[kCntOverflow], 1ull);
+        const bool ok = rasterThread(P, g, q, P.tileThreadBase[tileIndex] + column, generated, active);
+        if (active && generated > 0) atomicAdd(&P.counters[kCntThresholds], (unsigned long long)generated);
+        if (active && !ok) atomicAdd(&P.counters[kCntOverflow], 1ull);
     }
 }
 
