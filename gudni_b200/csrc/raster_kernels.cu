@@ -381,6 +381,11 @@ __global__ void strand_bounds_kernel(const uint8_t* __restrict__ geometry, size_
             lo = fminf(lo, p.y);
             hi = fmaxf(hi, p.y);
             infinite |= fabsf(p.x) == INFINITY || fabsf(p.y) == INFINITY;   // NaN terminates (and compares false)
+#ifdef GUDNI_SEARCH_X
+            // the x of every tree node (records 2.. of the strand), in the slot of this array that belongs to the node's
+            // record: an x-only copy of the tree for the searches, which compare nothing else (strandSearchX)
+            if (k >= 4 && !(k & 1)) bounds[(at >> 4) + (k >> 1)].x = p.x;
+#endif
         }
         bounds[at >> 4] = make_float2(lo, hi);
         at += 8ull * size;

@@ -269,7 +269,11 @@ __device__ __forceinline__ void generateTileThresholds(const FrameParams& P, Til
             uint32_t flags = 0u;
             if (tile.left + itemColumn < P.width) {
                 Trav l, r;
+#ifdef GUDNI_SEARCH_X
+                if (strandSearchX(P.geometry + 16ull * en.offset16, P.strandBounds + en.offset16 + 2, en.sizeWord, (float)(tile.left + itemColumn), en.right, en.lc, l, r)) {
+#else
                 if (strandSearch(P.geometry + 16ull * en.offset16, en.sizeWord, (float)(tile.left + itemColumn), en.right, en.lc, l, r)) {
+#endif
                     const float ymin = fminf(fminf(fminf(l.ly, l.cy), fminf(l.ry, r.ly)), fminf(r.cy, r.ry));
                     const float ymax = fmaxf(fmaxf(fmaxf(l.ly, l.cy), fmaxf(l.ry, r.ly)), fmaxf(r.cy, r.ry));
                     const bool noNaN = (l.ly == l.ly) && (l.cy == l.cy) && (l.ry == l.ry) && (r.ly == r.ly) && (r.cy == r.cy) && (r.ry == r.ry);
