@@ -155,6 +155,17 @@ def test_input_cache_skips_unchanged_uploads(rasterizer):
     assert np.array_equal(fresh, plain) and not np.array_equal(fresh, first)
 
 
+def test_replay_of_more_threads_than_it_has_queue_slots(rasterizer):
+    """More replayed column-threads than the replay kernel's 148 x 128 HBM queue slots: it goes round more than once, and
+    the frame after gets a slot per thread (frame_end grows the queues): same pixels both times."""
+    scene = scenes.fuzzy_circles(9000, 160, 160, 5, 40, 0xB177)
+    img, stats, ref = level2_parity(rasterizer, scene)
+    assert stats.n_spilled_threads > 148 * 128
+    img2, stats2 = rasterizer.raster_scene(1, scene)
+    assert stats2.n_spilled_threads == stats.n_spilled_threads
+    assert np.array_equal(img2, ref.image)
+
+
 def test_frame_stored_straight_into_a_host_bitmap(rasterizer):
     """gudni_b200_frame_target_host: the kernels' pixel stores go to a page-locked host bitmap; frame_end with the same
     pointer copies nothing; the pixels equal those of a frame rendered in HBM.  An unregistered bitmap is refused."""
